@@ -1,0 +1,8 @@
+"""b200sr3 — B200-native drop-in for the SR3 sampling path of
+zouiner/3d-super-resolution-Face-reconstruction (define_G / GaussianDiffusion)."""
+from .networks import define_G                      # noqa: F401
+from .diffusion import GaussianDiffusion, make_beta_schedule   # noqa: F401
+from .unet import UNet                              # noqa: F401
+from . import configs                               # noqa: F401
+
+__all__ = ["define_G", "GaussianDiffusion", "UNet", "make_beta_schedule", "configs"]

@@ -1,0 +1,210 @@
+// extern "C" surface declared in include/b200sr3.h. Exceptions never cross the boundary: they
+// are turned into a non-zero return code plus a thread-local message.
+#include <cstring>
+#include <string>
+
+#include "engine.cuh"
+
+using namespace b200sr3;
+
+struct b200sr3_handle {
+  Engine* engine;
+};
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    cudaGetLastError();   // clear a sticky-less launch error so the next call starts clean
+    return 1;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return 2;
+  }
+}
+
+static Engine& E(b200sr3_handle* h) {
+  if (!h || !h->engine) throw Error("null handle");
+  return *h->engine;
+}
+
+extern "C" {
+
+const char* b200sr3_last_error(void) { return g_last_error.c_str(); }
+int b200sr3_abi_version(void) { return B200SR3_ABI_VERSION; }
+
+int b200sr3_create(const b200sr3_config* cfg, int device, b200sr3_handle** out) {
+  return guarded([&] {
+    REQUIRE(cfg && out, "create: null argument");
+    *out = nullptr;
+    Engine* e = new Engine(*cfg, device);
+    *out = new b200sr3_handle{e};
+  });
+}
+
+int b200sr3_destroy(b200sr3_handle* h) {
+  return guarded([&] {
+    if (!h) return;
+    delete h->engine;
+    delete h;
+  });
+}
+
+int b200sr3_num_tensors(b200sr3_handle* h) {
+  int n = -1;
+  guarded([&] { n = E(h).num_tensors(); });
+  return n;
+}
+
+int b200sr3_tensor_info(b200sr3_handle* h, int index, const char** key, int64_t shape[4], int* ndim) {
+  return guarded([&] {
+    const TensorSpec& t = E(h).tensor(index);
+    if (key) *key = t.key.c_str();
+    if (ndim) *ndim = (int)t.shape.size();
+    if (shape)
+      for (size_t i = 0; i < 4; ++i) shape[i] = i < t.shape.size() ? t.shape[i] : 1;
+  });
+}
+
+int b200sr3_load_tensor(b200sr3_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  return guarded([&] {
+    REQUIRE(key && shape, "load_tensor: null argument");
+    E(h).load_tensor(key, data, shape, ndim);
+  });
+}
+
+int b200sr3_finalize_weights(b200sr3_handle* h, void* stream) {
+  return guarded([&] { E(h).finalize_weights((cudaStream_t)stream); });
+}
+
+int b200sr3_set_schedule(b200sr3_handle* h, int T, const float* sqrt_recip_ac, const float* sqrt_recipm1_ac,
+                         const float* coef1, const float* coef2, const float* post_logvar,
+                         const double* sqrt_ac_prev, void* stream) {
+  return guarded([&] {
+    E(h).set_schedule(T, sqrt_recip_ac, sqrt_recipm1_ac, coef1, coef2, post_logvar, sqrt_ac_prev, (cudaStream_t)stream);
+  });
+}
+
+int b200sr3_unet_forward(b200sr3_handle* h, const float* cond, const float* x, float noise_level, int B, int R,
+                         float* eps, void* stream) {
+  return guarded([&] { E(h).unet_forward(cond, x, noise_level, B, R, eps, (cudaStream_t)stream); });
+}
+
+int b200sr3_step(b200sr3_handle* h, const float* cond, const float* x_t, const float* noise, int t, int B, int R,
+                 float* x_tm1, void* stream) {
+  return guarded([&] { E(h).step(cond, x_t, noise, t, B, R, x_tm1, (cudaStream_t)stream); });
+}
+
+int b200sr3_sample(b200sr3_handle* h, const float* cond, int noise_mode, const float* noise, uint64_t seed, int B,
+                   int R, float* out, float* snapshots, void* stream) {
+  return guarded([&] { E(h).sample(cond, noise_mode, noise, seed, B, R, out, snapshots, (cudaStream_t)stream); });
+}
+
+int b200sr3_num_snapshots(b200sr3_handle* h) {
+  int n = -1;
+  guarded([&] { n = E(h).num_snapshots(); });
+  return n;
+}
+
+int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int B, int R, float* out_host,
+                        void* stream) {
+  return guarded([&] { E(h).sample_host(cond_host, seed, B, R, out_host, (cudaStream_t)stream); });
+}
+
+int b200sr3_layer_output(b200sr3_handle* h, const char* layer, float* dst, int* C, int* H, int* W, void* stream) {
+  return guarded([&] {
+    REQUIRE(layer, "layer_output: null name");
+    E(h).layer_output(layer, dst, C, H, W, (cudaStream_t)stream);
+  });
+}
+
+int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int64_t* conv) {
+  return guarded([&] {
+    if (total) *total = E(h).last_total;
+    if (conv) *conv = E(h).last_conv;
+  });
+}
+
+int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias, const float* residual, int B,
+                   int Cin, int H, int W, int Cout, int k, int stride, int upsample2x, float* y, int iters,
+                   float* avg_ms, void* stream) {
+  return guarded([&] {
+    REQUIRE(x && w && y, "conv2d: null pointer");
+    REQUIRE(k == 1 || k == 3, "conv2d: k must be 1 or 3");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(std::string("no CUDA device available (") + cudaGetErrorString(e) + "): no CPU fallback");
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major == 10, "conv2d: device is not sm_100");
+    CUDA_CHECK(cudaSetDevice(device));
+    conv_init_device();
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) {
+      void* p = nullptr;
+      CUDA_CHECK(cudaMalloc(&p, bytes));
+      tmp.push_back(p);
+      return p;
+    };
+    struct Cleanup {
+      std::vector<void*>& v;
+      ~Cleanup() { for (void* p : v) cudaFree(p); }
+    } cleanup{tmp};
+
+    Act in;
+    in.B = B; in.H = H; in.W = W; in.C = Cin;
+    in.ptr = (bf16*)dalloc(in.elems() * sizeof(bf16));
+    launch_nchw_to_nhwc(x, in.ptr, B, Cin, H, W, s);
+    Act src = in;
+    if (upsample2x) {
+      src.H = 2 * H; src.W = 2 * W;
+      src.ptr = (bf16*)dalloc(src.elems() * sizeof(bf16));
+      launch_upsample2x(in.ptr, src.ptr, B, H, W, Cin, s);
+    }
+    Act out;
+    out.B = B; out.H = src.H / stride; out.W = src.W / stride; out.C = Cout;
+    out.ptr = (bf16*)dalloc(out.elems() * sizeof(bf16));
+    bf16* res = nullptr;
+    if (residual) {
+      res = (bf16*)dalloc(out.elems() * sizeof(bf16));
+      launch_nchw_to_nhwc(residual, res, B, Cout, out.H, out.W, s);
+    }
+    PackedConv pc;
+    const int taps = k * k;
+    const int cpad = (Cin + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;
+    pc.cout = Cout; pc.taps = taps; pc.cin_main = Cin; pc.k_total = taps * cpad;
+    pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
+    launch_pack_conv_weight(w, pc.w, Cout, Cin, taps, cpad, 0, pc.k_total, s);
+    ConvSource cs;
+    cs.act = src; cs.taps = taps; cs.stride = stride;
+    int force_bn = 0;
+    if (const char* g = getenv("B200SR3_BLOCK_N")) force_bn = atoi(g);
+    Op op = make_conv_op("conv2d", cs, nullptr, nullptr, pc, bias, 0, nullptr, res, out, force_bn);
+    op.run(s);
+    launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (iters > 0 && avg_ms) {
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, s));
+      for (int i = 0; i < iters; ++i) op.run(s);
+      CUDA_CHECK(cudaEventRecord(e1, s));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      *avg_ms = ms / iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  });
+}
+
+}  // extern "C"

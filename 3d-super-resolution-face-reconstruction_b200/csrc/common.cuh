@@ -1,0 +1,80 @@
+// Shared declarations for the b200sr3 CUDA engine (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#ifndef __CUDA_ARCH__
+#define B200_HOST 1
+#endif
+
+namespace b200sr3 {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------- errors
+struct Error : std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CUDA_CHECK(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      throw ::b200sr3::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +      \
+                             " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")");         \
+  } while (0)
+
+#define REQUIRE(cond, msg)                                                                    \
+  do {                                                                                        \
+    if (!(cond)) throw ::b200sr3::Error(std::string(msg) + " [" #cond "]");                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------- step control
+// Lives in device memory; every kernel of a captured step reads it, so one CUDA graph serves
+// all T steps. Written by the host before a chain, advanced on the device after each step.
+struct StepCtl {
+  int t;               // current timestep (row of the schedule / noise-bias tables)
+  int T;               // schedule length; row T of the bias table is the scratch row
+  int noise_mode;      // 0: zeros, 1: injected list, 2: philox, 3: direct pointer (one step)
+  int pad;
+  const float* noise;  // list base (mode 1) or this step's z (mode 3)
+  unsigned long long seed;
+  long long numel;     // B*3*R*R, stride between entries of the injected list
+};
+
+// ------------------------------------------------------------------------------- small helpers
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct Act {  // NHWC bf16 activation
+  bf16* ptr = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t elems() const { return (size_t)B * H * W * C; }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+#endif
+
+}  // namespace b200sr3

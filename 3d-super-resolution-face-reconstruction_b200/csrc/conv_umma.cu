@@ -1,0 +1,177 @@
+// Host side of the tcgen05 implicit-GEMM convolution: TMA descriptor construction, tile-shape
+// choice and the launch closure. The kernel itself is in conv_umma.cuh.
+#include <memory>
+#include <mutex>
+
+#include "engine.cuh"
+
+namespace b200sr3 {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time so that the library still loads (symbols only) on a host
+// without a driver.
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 activation: dims (C, W', H', B) with arbitrary element strides so
+// that the stride-2 "parity" views can be expressed; box = (64, bw, bh, bb), 128B swizzle.
+static void encode_act_map(CUtensorMap* m, const bf16* base, int C, int Wd, int Hd, int Bd, size_t sw,
+                           size_t sh, size_t sb, int bw, int bh, int bb) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Bd};
+  cuuint64_t strides[3] = {(cuuint64_t)(sw * 2), (cuuint64_t)(sh * 2), (cuuint64_t)(sb * 2)};
+  cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error("cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string((int)r));
+}
+
+static void encode_weight_map(CUtensorMap* m, const bf16* w, int k_total, int cout, int block_n) {
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <int BN, int ST>
+static void launch_conv(const ConvParams& p, dim3 grid, cudaStream_t s) {
+  conv_umma_kernel<BN, ST><<<grid, CONV_THREADS, ConvSmem<BN, ST>::TOTAL, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void conv_init_device() {
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<64, 4>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<128, 3>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<256, 4>::TOTAL));
+}
+
+Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0, const Act* res1,
+                const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl,
+                const bf16* residual, const Act& out, int force_block_n) {
+  const Act& a = main.act;
+  REQUIRE(main.stride == 1 || main.stride == 2, "conv: stride must be 1 or 2");
+  REQUIRE(main.taps == 9 || main.taps == 1, "conv: kernel must be 1x1 or 3x3");
+  REQUIRE(a.C % 8 == 0 && out.C % 8 == 0, "conv: channel counts must be multiples of 8");
+  REQUIRE(a.C == w.cin_main && out.C == w.cout && main.taps == w.taps, "conv: weight/activation mismatch");
+  REQUIRE(out.H * main.stride == a.H && out.W * main.stride == a.W && out.B == a.B, "conv: output shape mismatch");
+  REQUIRE(is_pow2(out.W) && is_pow2(out.H), "conv: spatial dims must be powers of two");
+
+  auto pp = std::make_shared<ConvParams>();
+  ConvParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  // ---- tile box over the output pixels
+  p.bw = std::min(out.W, CONV_BLOCK_M);
+  p.bh = std::min(out.H, CONV_BLOCK_M / p.bw);
+  p.bb = CONV_BLOCK_M / (p.bw * p.bh);
+  p.tiles_w = out.W / p.bw;
+  p.tiles_h = out.H / p.bh;
+  p.tiles_b = ceil_div(out.B, p.bb);
+  p.B = out.B; p.Hout = out.H; p.Wout = out.W; p.Cout = out.C;
+  p.out_sy = p.out_sx = 1; p.out_oy = p.out_ox = 0;
+  p.out_H = out.H; p.out_W = out.W;
+  p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
+  p.residual = residual; p.out = out.ptr;
+
+  // ---- A maps + tap list (order must match the packed weight's K order)
+  int nt = 0, kblocks = 0;
+  const int cb_main = ceil_div(a.C, CONV_BLOCK_K);
+  if (main.stride == 1) {
+    encode_act_map(&p.a_map[0], a.ptr, a.C, a.W, a.H, a.B, (size_t)a.C, (size_t)a.W * a.C,
+                   (size_t)a.H * a.W * a.C, p.bw, p.bh, p.bb);
+    for (int t = 0; t < main.taps; ++t) {
+      ConvTap& tp = p.taps[nt++];
+      tp.map = 0;
+      tp.dh = main.taps == 9 ? (int16_t)(t / 3 - 1) : 0;
+      tp.dw = main.taps == 9 ? (int16_t)(t % 3 - 1) : 0;
+      tp.cblocks = (int16_t)cb_main;
+      kblocks += cb_main;
+    }
+  } else {
+    REQUIRE(main.taps == 9 && !res0 && !res1, "conv: stride 2 supports plain 3x3 only");
+    // parity view (ph, pw): element (c, j, i, b) = src[b][2i+ph][2j+pw][c]
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        encode_act_map(&p.a_map[ph * 2 + pw], a.ptr + ((size_t)ph * a.W + pw) * a.C, a.C, a.W / 2, a.H / 2, a.B,
+                       (size_t)2 * a.C, (size_t)2 * a.W * a.C, (size_t)a.H * a.W * a.C, p.bw, p.bh, p.bb);
+    for (int t = 0; t < 9; ++t) {
+      const int kh = t / 3, kw = t % 3;       // input row = 2*ho + kh - 1
+      ConvTap& tp = p.taps[nt++];
+      tp.map = (int16_t)(((kh == 1) ? 0 : 1) * 2 + ((kw == 1) ? 0 : 1));
+      tp.dh = (kh == 0) ? -1 : 0;
+      tp.dw = (kw == 0) ? -1 : 0;
+      tp.cblocks = (int16_t)cb_main;
+      kblocks += cb_main;
+    }
+  }
+  const Act* rs[2] = {res0, res1};
+  const int rc[2] = {w.c_res0, w.c_res1};
+  for (int i = 0; i < 2; ++i) {
+    if (!rs[i]) { REQUIRE(rc[i] == 0, "conv: missing res_conv source"); continue; }
+    REQUIRE(rs[i]->C == rc[i] && rs[i]->H == out.H && rs[i]->W == out.W && rs[i]->B == out.B,
+            "conv: res_conv source mismatch");
+    const Act& r = *rs[i];
+    encode_act_map(&p.a_map[1 + i], r.ptr, r.C, r.W, r.H, r.B, (size_t)r.C, (size_t)r.W * r.C,
+                   (size_t)r.H * r.W * r.C, p.bw, p.bh, p.bb);
+    ConvTap& tp = p.taps[nt++];
+    tp.map = (int16_t)(1 + i); tp.dh = 0; tp.dw = 0;
+    tp.cblocks = (int16_t)ceil_div(r.C, CONV_BLOCK_K);
+    kblocks += tp.cblocks;
+  }
+  REQUIRE(nt <= CONV_MAX_TAPS, "conv: too many taps");
+  REQUIRE(kblocks * CONV_BLOCK_K == w.k_total, "conv: packed weight K does not match the tap list");
+  p.num_taps = nt;
+  p.num_kblocks = kblocks;
+
+  // ---- N tile: largest of 256/128/64 that divides Cout and still yields >= 148 CTAs
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  int bn = 64;
+  if (force_block_n) {
+    bn = force_block_n;
+  } else {
+    const int cand[3] = {256, 128, 64};
+    for (int c : cand) {
+      if (out.C % c != 0) continue;
+      if (m_tiles * (out.C / c) >= 148 || c == 64) { bn = c; break; }
+    }
+  }
+  REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BLOCK_N must be 64, 128 or 256");
+  encode_weight_map(&p.w_map, w.w, w.k_total, w.cout, bn);
+  const dim3 grid(m_tiles, ceil_div(out.C, bn));
+
+  Op op;
+  op.name = name;
+  op.is_conv = true;
+  op.run = [pp, grid, bn](cudaStream_t s) {
+    if (bn == 256) launch_conv<256, 4>(*pp, grid, s);
+    else if (bn == 128) launch_conv<128, 3>(*pp, grid, s);
+    else launch_conv<64, 4>(*pp, grid, s);
+  };
+  return op;
+}
+
+}  // namespace b200sr3

@@ -1,0 +1,332 @@
+// Implicit-GEMM convolution on Blackwell tensor cores (tcgen05.mma, TMEM accumulators, TMA).
+//
+// Replaces every nn.Conv2d of the reference UNet (model/sr/sr3_modules/unet.py:62,71,87,102,
+// 120-121) except the 6->64 head and the 64->3 tail, which are CUDA-core kernels.
+//
+// GEMM view:  D[M, N] = A[M, K] * W[N, K]^T
+//   M = output pixels. One CTA owns 128 of them, chosen as a (bb x bh x bw) box of the NHWC
+//       activation so that ONE 4-D TMA box load, shifted by the filter tap, fetches the
+//       A tile of that tap: rows = pixels, 64 channels (128 B) per row, 128B-swizzled — i.e.
+//       exactly the K-major SWIZZLE_128B operand layout tcgen05 wants. Out-of-bounds rows/cols
+//       (the conv's zero padding, or batch rows past B) are zero-filled by the TMA unit.
+//   N = output channels, BLOCK_N per CTA (64/128/256) = TMEM columns of the fp32 accumulator.
+//   K = sum over "taps" of 64-channel blocks: the 9 (or 1) filter taps of the main source,
+//       then optional 1x1 segments of other sources (the ResnetBlock's res_conv folded into
+//       block2's GEMM, unet.py:103-110). Weights are pre-packed [Cout][K] in the same order.
+// Stride-2 convs use four "parity" tensor maps over the same buffer (base offset + doubled
+// strides) so a tap is again one plain box load.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> +bias (+residual) -> bf16).
+#pragma once
+#include "common.cuh"
+
+namespace b200sr3 {
+
+constexpr int CONV_BLOCK_M = 128;
+constexpr int CONV_BLOCK_K = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr int CONV_MAX_TAPS = 12;
+constexpr int CONV_THREADS = 256;
+
+struct ConvTap {
+  int16_t map;      // which A tensor map
+  int16_t dw, dh;   // box origin shift in the source's (W, H) index space
+  int16_t cblocks;  // number of 64-channel K blocks this tap contributes
+};
+
+struct alignas(64) ConvParams {
+  CUtensorMap a_map[4];
+  CUtensorMap w_map;
+  ConvTap taps[CONV_MAX_TAPS];
+  int num_taps;
+  int num_kblocks;
+  int tiles_w, tiles_h, tiles_b;   // tile grid over the OUTPUT pixels
+  int bw, bh, bb;                  // box (tile) extent in pixels, bw*bh*bb == 128
+  int B, Hout, Wout, Cout;         // output tensor [B, Hout, Wout, Cout] bf16 NHWC
+  int out_sy, out_sx, out_oy, out_ox;  // output pixel = (h*out_sy + out_oy, w*out_sx + out_ox)
+  int out_H, out_W;                // dims of the tensor `out` points at (differs when scattering)
+  const float* bias;               // [Cout] (may be null)
+  int bias_t_stride;               // if non-zero, row ctl->t of a [rows][stride] table is used
+  const StepCtl* ctl;
+  const bf16* residual;            // same shape as out, added in the epilogue (may be null)
+  bf16* out;
+};
+
+#ifdef __CUDACC__
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (-> cudaErrorLaunchFailure), never as a
+// hung GPU. ~2 s at 2 GHz.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b200sr3: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, single CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 64 bf16 (128 B),
+// 8-row groups 1024 B apart (SBO); LBO is unused for swizzled K-major layouts (encoded as 1);
+// bits [46,48) = descriptor version 1 (Blackwell); bits [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+}  // namespace ptx
+
+template <int BLOCK_N, int STAGES>
+struct ConvSmem {
+  static constexpr int A_BYTES = CONV_BLOCK_M * CONV_BLOCK_K * 2;   // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * CONV_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;            // + barriers + align slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ ConvParams p) {
+  using S = ConvSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full; then the TMEM address.
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int m_tile = blockIdx.x;
+  const int tw = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int th = m_tile % p.tiles_h;
+  const int tb = m_tile / p.tiles_h;
+  const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.bb;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.w_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, BLOCK_N);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      int stage = 0, kb = 0;
+      uint32_t phase = 0;
+      for (int ti = 0; ti < p.num_taps; ++ti) {
+        const ConvTap tap = p.taps[ti];
+        const CUtensorMap* amap = &p.a_map[tap.map];
+        for (int cb = 0; cb < tap.cblocks; ++cb, ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+          ptx::mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+          ptx::tma_load_4d(sa, amap, full_bar(stage), cb * CONV_BLOCK_K, w0 + tap.dw, h0 + tap.dh, b0);
+          ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < CONV_BLOCK_K / 16; ++k) {
+          // advancing 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in the address field
+          const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
+          const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
+          ptx::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int wq = warp & 3;                  // TMEM lane quarter this warp may read
+    const int row = wq * 32 + lane;           // GEMM row = pixel inside the box
+    const int lw = row % p.bw;
+    const int lh = (row / p.bw) % p.bh;
+    const int lb = row / (p.bw * p.bh);
+    const int b = b0 + lb, h = h0 + lh, w = w0 + lw;
+    const bool valid = (b < p.B) && (h < p.Hout) && (w < p.Wout);
+    const size_t pix = ((size_t)b * p.out_H + (size_t)(h * p.out_sy + p.out_oy)) * p.out_W +
+                       (size_t)(w * p.out_sx + p.out_ox);
+    bf16* out_row = p.out + pix * p.Cout + n0;
+    const bf16* res_row = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+    const float* bias = p.bias;
+    if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int n = n0 + c0 + j;
+          if (n < p.Cout) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+            if (bias) {
+              const float4 b0v = __ldg(reinterpret_cast<const float4*>(bias + n));
+              const float4 b1v = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+              f[0] += b0v.x; f[1] += b0v.y; f[2] += b0v.z; f[3] += b0v.w;
+              f[4] += b1v.x; f[5] += b1v.y; f[6] += b1v.z; f[7] += b1v.w;
+            }
+            if (res_row) {
+              float r[8];
+              unpack8(*reinterpret_cast<const uint4*>(res_row + c0 + j), r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += r[e];
+            }
+            *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, BLOCK_N);
+}
+#endif  // __CUDACC__
+
+}  // namespace b200sr3

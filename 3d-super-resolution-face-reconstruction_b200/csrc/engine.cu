@@ -1,0 +1,672 @@
+// Engine: mirrors UNet.__init__/forward (model/sr/sr3_modules/unet.py:161-265) and
+// GaussianDiffusion.p_sample_loop (model/sr/sr3_modules/diffusion.py:189-215) as a static
+// launch plan over NHWC bf16 buffers.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace b200sr3 {
+
+// ------------------------------------------------------------------------------- tiny kernels
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
+}
+static void add_vec(const float* a, const float* b, float* o, int n, cudaStream_t s) {
+  add_vec_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, o, n);
+  CUDA_CHECK(cudaGetLastError());
+}
+// OIHW fp32 (channel slice [c0, c0+cseg) of cin_total) -> packed bf16 K-major row segment.
+__global__ void pack_slice_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int cseg, int c0,
+                                  int cin_total, int taps, int cpad, int k_off, int k_total) {
+  const long long total = (long long)Cout * taps * cpad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cpad);
+    const int tap = (int)((idx / cpad) % taps);
+    const int o = (int)(idx / ((long long)cpad * taps));
+    const float v = (c < cseg) ? src[((size_t)o * cin_total + c0 + c) * taps + tap] : 0.f;
+    dst[(size_t)o * k_total + k_off + tap * cpad + c] = __float2bfloat16_rn(v);
+  }
+}
+static void pack_slice(const float* src, bf16* dst, int Cout, int cseg, int c0, int cin_total, int taps, int cpad,
+                       int k_off, int k_total, cudaStream_t s) {
+  const long long total = (long long)Cout * taps * cpad;
+  const long long blocks = std::min<long long>((total + 255) / 256, 8192);
+  pack_slice_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, Cout, cseg, c0, cin_total, taps, cpad, k_off, k_total);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+Workspace::~Workspace() {
+  if (graph) cudaGraphExecDestroy(graph);
+  for (void* p : allocations) cudaFree(p);
+}
+
+// ------------------------------------------------------------------------------- construction
+Engine::Engine(const b200sr3_config& cfg, int device) : cfg_(cfg), device_(device) {
+  REQUIRE(cfg.n_mults >= 1 && cfg.n_mults <= B200SR3_MAX_LEVELS, "config: bad channel_multiplier length");
+  REQUIRE(cfg.n_attn_res >= 0 && cfg.n_attn_res <= B200SR3_MAX_LEVELS, "config: bad attn_res length");
+  REQUIRE(cfg.inner_channel % 8 == 0 && cfg.inner_channel >= 8, "config: inner_channel must be a multiple of 8");
+  REQUIRE(cfg.inner_channel % 2 == 0 && cfg.inner_channel <= 256, "config: inner_channel out of range");
+  REQUIRE(cfg.norm_groups >= 1 && cfg.norm_groups <= 64, "config: norm_groups out of range");
+  REQUIRE(cfg.out_channel == 1 || cfg.out_channel == 3 || cfg.out_channel == 4, "config: out_channel must be 1, 3 or 4");
+  REQUIRE(cfg.in_channel == (cfg.conditional ? 2 : 1) * cfg.out_channel,
+          "config: in_channel must be out_channel (x) plus out_channel (cond) when conditional");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                "): b200sr3 has no CPU fallback");
+  REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    throw Error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                std::to_string(prop.minor) + "; b200sr3 is built for sm_100a (B200) only");
+  CUDA_CHECK(cudaSetDevice(device));
+  conv_init_device();
+  CUDA_CHECK(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaMalloc(&ctl_, sizeof(StepCtl)));
+  CUDA_CHECK(cudaMemset(ctl_, 0, sizeof(StepCtl)));
+  if (const char* g = getenv("B200SR3_NO_GRAPH")) use_graph_ = !(g[0] == '1');
+  if (const char* g = getenv("B200SR3_BLOCK_N")) force_block_n_ = atoi(g);
+  build_layers();
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  workspaces_.clear();
+  for (auto& t : tensors_) if (t.dev) cudaFree(t.dev);
+  for (void* p : owned_) cudaFree(p);
+  if (coefs_) cudaFree(coefs_);
+  if (nl_) cudaFree(nl_);
+  if (table_) cudaFree(table_);
+  if (ctl_) cudaFree(ctl_);
+  if (capture_stream_) cudaStreamDestroy(capture_stream_);
+}
+
+void Engine::add_tensor(const std::string& key, std::vector<int64_t> shape) {
+  TensorSpec t;
+  t.key = key;
+  t.shape = std::move(shape);
+  tensor_index_[key] = (int)tensors_.size();
+  tensors_.push_back(std::move(t));
+}
+
+// Walks the reference constructor (unet.py:175-233) to produce the layer list and the
+// state_dict key set.
+void Engine::build_layers() {
+  const int inner = cfg_.inner_channel;
+  auto has_attn = [&](int res) {
+    for (int i = 0; i < cfg_.n_attn_res; ++i) if (cfg_.attn_res[i] == res) return true;
+    return false;
+  };
+  add_tensor("noise_level_mlp.1.weight", {4 * inner, inner});
+  add_tensor("noise_level_mlp.1.bias", {4 * inner});
+  add_tensor("noise_level_mlp.3.weight", {inner, 4 * inner});
+  add_tensor("noise_level_mlp.3.bias", {inner});
+
+  auto add_conv = [&](const std::string& k, int co, int ci, int ks, bool bias = true) {
+    add_tensor(k + ".weight", {co, ci, ks, ks});
+    if (bias) add_tensor(k + ".bias", {co});
+  };
+  auto add_gn = [&](const std::string& k, int c) {
+    add_tensor(k + ".weight", {c});
+    add_tensor(k + ".bias", {c});
+  };
+  auto add_res = [&](const std::string& name, int cx, int cskip, int cout, bool attn) {
+    const int cin = cx + cskip;
+    LayerDesc l{name, LayerKind::Res, cx, cskip, cout, attn};
+    layers_.push_back(l);
+    const std::string rb = name + ".res_block";
+    add_gn(rb + ".block1.block.0", cin);
+    add_conv(rb + ".block1.block.3", cout, cin, 3);
+    add_tensor(rb + ".noise_func.noise_func.0.weight", {cout, inner});
+    add_tensor(rb + ".noise_func.noise_func.0.bias", {cout});
+    add_gn(rb + ".block2.block.0", cout);
+    add_conv(rb + ".block2.block.3", cout, cout, 3);
+    if (cin != cout) add_conv(rb + ".res_conv", cout, cin, 1);
+    if (attn) {
+      add_gn(name + ".attn.norm", cout);
+      add_conv(name + ".attn.qkv", 3 * cout, cout, 1, false);
+      add_conv(name + ".attn.out", cout, cout, 1);
+    }
+    noise_off_[name] = noise_total_;
+    noise_total_ += round_up(cout, 8);
+  };
+
+  layers_.push_back(LayerDesc{"downs.0", LayerKind::HeadConv, cfg_.in_channel, 0, inner, false});
+  add_conv("downs.0", inner, cfg_.in_channel, 3);
+  int pre = inner, now_res = cfg_.image_size, idx = 1;
+  std::vector<int> feat{pre};
+  for (int lvl = 0; lvl < cfg_.n_mults; ++lvl) {
+    const bool last = lvl == cfg_.n_mults - 1;
+    const bool attn = has_attn(now_res);
+    const int ch = inner * cfg_.channel_mults[lvl];
+    for (int r = 0; r < cfg_.res_blocks; ++r) {
+      add_res("downs." + std::to_string(idx++), pre, 0, ch, attn);
+      feat.push_back(ch);
+      pre = ch;
+    }
+    if (!last) {
+      const std::string name = "downs." + std::to_string(idx++);
+      layers_.push_back(LayerDesc{name, LayerKind::Down, pre, 0, pre, false});
+      add_conv(name + ".conv", pre, pre, 3);
+      feat.push_back(pre);
+      now_res /= 2;
+    }
+  }
+  add_res("mid.0", pre, 0, pre, true);
+  add_res("mid.1", pre, 0, pre, false);
+  idx = 0;
+  for (int lvl = cfg_.n_mults - 1; lvl >= 0; --lvl) {
+    const bool last = lvl < 1;
+    const bool attn = has_attn(now_res);
+    const int ch = inner * cfg_.channel_mults[lvl];
+    for (int r = 0; r < cfg_.res_blocks + 1; ++r) {
+      const int sk = feat.back();
+      feat.pop_back();
+      add_res("ups." + std::to_string(idx++), pre, sk, ch, attn);
+      pre = ch;
+    }
+    if (!last) {
+      const std::string name = "ups." + std::to_string(idx++);
+      layers_.push_back(LayerDesc{name, LayerKind::Up, pre, 0, pre, false});
+      add_conv(name + ".conv", pre, pre, 3);
+      now_res *= 2;
+    }
+  }
+  layers_.push_back(LayerDesc{"final_conv", LayerKind::Final, pre, 0, cfg_.out_channel, false});
+  add_gn("final_conv.block.0", pre);
+  add_conv("final_conv.block.3", cfg_.out_channel, pre, 3);
+}
+
+void Engine::load_tensor(const std::string& key, const float* data, const int64_t* shape, int ndim) {
+  auto it = tensor_index_.find(key);
+  if (it == tensor_index_.end()) throw Error("load_tensor: unexpected key '" + key + "'");
+  TensorSpec& t = tensors_[it->second];
+  bool ok = (int)t.shape.size() == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = t.shape[i] == shape[i];
+  if (!ok) {
+    std::string want, got;
+    for (auto d : t.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    throw Error("load_tensor: shape mismatch for '" + key + "': expected [" + want + "] got [" + got + "]");
+  }
+  REQUIRE(data != nullptr, "load_tensor: null data");
+  CUDA_CHECK(cudaSetDevice(device_));
+  if (!t.dev) CUDA_CHECK(cudaMalloc(&t.dev, t.numel() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(t.dev, data, t.numel() * sizeof(float), cudaMemcpyDefault));
+  t.loaded = true;
+  finalized_ = false;
+}
+
+float* Engine::T_(const std::string& key) const {
+  auto it = tensor_index_.find(key);
+  if (it == tensor_index_.end()) throw Error("internal: unknown tensor '" + key + "'");
+  const TensorSpec& t = tensors_[it->second];
+  if (!t.loaded) throw Error("weights: tensor '" + key + "' was never loaded");
+  return t.dev;
+}
+
+void Engine::finalize_weights(cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  for (auto& t : tensors_)
+    if (!t.loaded) throw Error("finalize_weights: tensor '" + t.key + "' was never loaded");
+  workspaces_.clear();                 // plans hold pointers into the packed weights
+  for (void* p : owned_) cudaFree(p);
+  owned_.clear();
+  convs_.clear();
+  auto dalloc = [&](size_t bytes) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    owned_.push_back(p);
+    return p;
+  };
+  const int inner = cfg_.inner_channel;
+  wall_ = (float*)dalloc((size_t)noise_total_ * inner * sizeof(float));
+  ball_ = (float*)dalloc((size_t)noise_total_ * sizeof(float));
+  CUDA_CHECK(cudaMemsetAsync(wall_, 0, (size_t)noise_total_ * inner * sizeof(float), s));
+  CUDA_CHECK(cudaMemsetAsync(ball_, 0, (size_t)noise_total_ * sizeof(float), s));
+
+  // plain conv (optionally with folded 1x1 res segments appended along K)
+  auto pack = [&](const std::string& name, const std::string& wkey, int cout, int cin, int taps,
+                  const std::string& reskey, int c_res0, int c_res1) {
+    PackedConv pc;
+    pc.cout = cout; pc.taps = taps; pc.cin_main = cin; pc.c_res0 = c_res0; pc.c_res1 = c_res1;
+    const int cpad = round_up(cin, CONV_BLOCK_K);
+    const int r0pad = c_res0 ? round_up(c_res0, CONV_BLOCK_K) : 0;
+    const int r1pad = c_res1 ? round_up(c_res1, CONV_BLOCK_K) : 0;
+    pc.k_total = taps * cpad + r0pad + r1pad;
+    pc.w = (bf16*)dalloc((size_t)cout * pc.k_total * sizeof(bf16));
+    pack_slice(T_(wkey + ".weight"), pc.w, cout, cin, 0, cin, taps, cpad, 0, pc.k_total, s);
+    if (c_res0) pack_slice(T_(reskey + ".weight"), pc.w, cout, c_res0, 0, c_res0 + c_res1, 1, r0pad, taps * cpad, pc.k_total, s);
+    if (c_res1) pack_slice(T_(reskey + ".weight"), pc.w, cout, c_res1, c_res0, c_res0 + c_res1, 1, r1pad, taps * cpad + r0pad, pc.k_total, s);
+    convs_[name] = pc;
+    return &convs_[name];
+  };
+
+  for (const LayerDesc& l : layers_) {
+    switch (l.kind) {
+      case LayerKind::HeadConv: {
+        head_w_ = (float*)dalloc((size_t)l.cout * l.c_x * 9 * sizeof(float));
+        launch_pack_head_weight(T_(l.name + ".weight"), head_w_, l.cout, l.c_x, s);
+        break;
+      }
+      case LayerKind::Down:
+      case LayerKind::Up: {
+        PackedConv* pc = pack(l.name + ".conv", l.name + ".conv", l.cout, l.c_x, 9, "", 0, 0);
+        pc->bias = T_(l.name + ".conv.bias");
+        break;
+      }
+      case LayerKind::Final: {
+        tail_w_ = (float*)dalloc((size_t)l.cout * 9 * l.c_x * sizeof(float));
+        launch_pack_tail_weight(T_(l.name + ".block.3.weight"), tail_w_, l.cout, l.c_x, s);
+        break;
+      }
+      case LayerKind::Res: {
+        const std::string rb = l.name + ".res_block";
+        const int cin = l.c_x + l.c_skip;
+        pack(l.name + ".c1", rb + ".block1.block.3", l.cout, cin, 9, "", 0, 0);
+        // conv1's bias and the FeatureWiseAffine bias both land in the per-timestep table
+        const int off = noise_off_[l.name];
+        CUDA_CHECK(cudaMemcpyAsync(wall_ + (size_t)off * inner, T_(rb + ".noise_func.noise_func.0.weight"),
+                                   (size_t)l.cout * inner * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        add_vec(T_(rb + ".noise_func.noise_func.0.bias"), T_(rb + ".block1.block.3.bias"), ball_ + off, l.cout, s);
+        const bool has_res = cin != l.cout;
+        PackedConv* c2 = pack(l.name + ".c2", rb + ".block2.block.3", l.cout, l.cout, 9, rb + ".res_conv",
+                              has_res ? l.c_x : 0, has_res ? l.c_skip : 0);
+        c2->bias = (float*)dalloc((size_t)l.cout * sizeof(float));
+        add_vec(T_(rb + ".block2.block.3.bias"), has_res ? T_(rb + ".res_conv.bias") : nullptr, c2->bias, l.cout, s);
+        if (!has_res) REQUIRE(l.c_skip == 0, "identity residual over a concatenated input is not supported");
+        if (l.attn) {
+          pack(l.name + ".qkv", l.name + ".attn.qkv", 3 * l.cout, l.cout, 1, "", 0, 0);
+          PackedConv* o = pack(l.name + ".out", l.name + ".attn.out", l.cout, l.cout, 1, "", 0, 0);
+          o->bias = T_(l.name + ".attn.out.bias");
+        }
+        break;
+      }
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  finalized_ = true;
+  // the bias table depends on the weights: rebuild it if a schedule is already installed
+  if (table_) {
+    NoiseTablePlan np{nl_, T_("noise_level_mlp.1.weight"), T_("noise_level_mlp.1.bias"),
+                      T_("noise_level_mlp.3.weight"), T_("noise_level_mlp.3.bias"), wall_, ball_, inner,
+                      noise_total_, table_};
+    launch_noise_table(np, 0, T_sched_, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+}
+
+void Engine::set_schedule(int T, const float* a, const float* bc, const float* c1, const float* c2,
+                          const float* lv, const double* sqrt_ac_prev, cudaStream_t s) {
+  REQUIRE(T >= 1, "set_schedule: T must be positive");
+  REQUIRE(a && bc && c1 && c2 && lv && sqrt_ac_prev, "set_schedule: null table");
+  CUDA_CHECK(cudaSetDevice(device_));
+  if (coefs_) cudaFree(coefs_);
+  if (nl_) cudaFree(nl_);
+  if (table_) cudaFree(table_);
+  coefs_ = nl_ = table_ = nullptr;
+  T_sched_ = T;
+  std::vector<float> h((size_t)5 * T);
+  const float* src[5] = {a, bc, c1, c2, lv};
+  for (int k = 0; k < 5; ++k) memcpy(h.data() + (size_t)k * T, src[k], (size_t)T * sizeof(float));
+  CUDA_CHECK(cudaMalloc(&coefs_, h.size() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(coefs_, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // diffusion.py:166-167: noise_level for step t is float32(sqrt_alphas_cumprod_prev[t+1])
+  std::vector<float> nl((size_t)T + 1, 0.f);
+  for (int t = 0; t < T; ++t) nl[t] = (float)sqrt_ac_prev[t + 1];
+  CUDA_CHECK(cudaMalloc(&nl_, nl.size() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(nl_, nl.data(), nl.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&table_, (size_t)(T + 1) * noise_total_ * sizeof(float)));
+  workspaces_.clear();                 // plans captured the old table pointers
+  if (finalized_) {
+    NoiseTablePlan np{nl_, T_("noise_level_mlp.1.weight"), T_("noise_level_mlp.1.bias"),
+                      T_("noise_level_mlp.3.weight"), T_("noise_level_mlp.3.bias"), wall_, ball_,
+                      cfg_.inner_channel, noise_total_, table_};
+    launch_noise_table(np, 0, T, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+}
+
+int Engine::num_snapshots() const {
+  if (T_sched_ <= 0) return 0;
+  const int inter = 1 | (T_sched_ / 10);
+  int n = 0;
+  for (int t = 0; t < T_sched_; ++t) n += (t % inter == 0);
+  return n;
+}
+
+// ------------------------------------------------------------------------------- workspace
+Workspace& Engine::workspace(int B, int R) {
+  REQUIRE(finalized_, "weights are not finalized (call b200sr3_finalize_weights)");
+  REQUIRE(B >= 1 && R >= 1, "B and R must be positive");
+  REQUIRE((R & (R - 1)) == 0, "R must be a power of two");
+  REQUIRE((R >> (cfg_.n_mults - 1)) >= 1, "R is too small for the number of UNet levels");
+  if (!table_) {          // no schedule yet: a one-row (scratch) table so unet_forward works
+    T_sched_ = 0;
+    CUDA_CHECK(cudaMalloc(&nl_, sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&table_, (size_t)noise_total_ * sizeof(float)));
+  }
+  auto key = std::make_pair(B, R);
+  auto it = workspaces_.find(key);
+  if (it != workspaces_.end()) return *it->second;
+  std::unique_ptr<Workspace> ws(new Workspace());
+  ws->B = B;
+  ws->R = R;
+  build_workspace(*ws);
+  Workspace& ref = *ws;
+  workspaces_[key] = std::move(ws);
+  return ref;
+}
+
+void Engine::build_workspace(Workspace& ws) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  const int B = ws.B, R = ws.R;
+  auto dalloc = [&](size_t bytes) {
+    void* p = nullptr;
+    bytes = (bytes + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess)
+      throw Error("workspace allocation of " + std::to_string(bytes) + " bytes failed after " +
+                  std::to_string(ws.bytes) + ": " + cudaGetErrorString(e));
+    ws.allocations.push_back(p);
+    ws.bytes += bytes;
+    return p;
+  };
+  auto act = [&](int H, int W, int C) {
+    Act a;
+    a.B = B; a.H = H; a.W = W; a.C = C;
+    a.ptr = (bf16*)dalloc(a.elems() * sizeof(bf16));
+    return a;
+  };
+  const int oc = cfg_.out_channel;
+  const size_t img = (size_t)B * oc * R * R * sizeof(float);
+  ws.cond = (float*)dalloc(img);
+  ws.x = (float*)dalloc(img);
+  ws.eps = (float*)dalloc(img);
+  CUDA_CHECK(cudaMemset(ws.cond, 0, img));
+  const int G = cfg_.norm_groups;
+
+  // GroupNorm (+Swish) of [x0 | x1] into a fresh tensor; two launches.
+  auto group_norm = [&](const std::string& name, const Act& x0, const Act* x1, const std::string& gkey, bool swish) {
+    auto g = std::make_shared<GnPlan>();
+    g->src0 = x0.ptr; g->C0 = x0.C;
+    g->src1 = x1 ? x1->ptr : nullptr; g->C1 = x1 ? x1->C : 0;
+    g->B = B; g->HW = x0.H * x0.W; g->groups = G;
+    const int C = g->C0 + g->C1;
+    REQUIRE(C % G == 0, "GroupNorm: channels not divisible by norm_groups");
+    g->gamma = T_(gkey + ".weight");
+    g->beta = T_(gkey + ".bias");
+    gn_choose_chunks(*g);
+    g->partial = (float*)dalloc((size_t)B * g->chunks * C * 2 * sizeof(float));
+    g->scale_shift = (float*)dalloc((size_t)B * C * 2 * sizeof(float));
+    g->ticket = (int*)dalloc((size_t)B * sizeof(int));
+    CUDA_CHECK(cudaMemset(g->ticket, 0, (size_t)B * sizeof(int)));
+    Act y = act(x0.H, x0.W, C);
+    g->dst = y.ptr;
+    g->swish = swish ? 1 : 0;
+    ws.ops.push_back(Op{name + ".gn_stats", false, [g](cudaStream_t s) { launch_gn_stats(*g, s); }});
+    ws.ops.push_back(Op{name + ".gn_apply", false, [g](cudaStream_t s) { launch_gn_apply(*g, s); }});
+    return y;
+  };
+  auto conv = [&](const std::string& name, const Act& src, int taps, int stride, const PackedConv& w,
+                  const Act* r0, const Act* r1, const float* bias, int bias_stride, const bf16* residual,
+                  int Ho, int Wo) {
+    Act y = act(Ho, Wo, w.cout);
+    ConvSource cs;
+    cs.act = src; cs.taps = taps; cs.stride = stride;
+    ws.ops.push_back(make_conv_op(name, cs, r0, r1, w, bias, bias_stride, ctl_, residual, y, force_block_n_));
+    ws.n_conv++;
+    return y;
+  };
+
+  std::vector<Act> feats;
+  Act cur;
+  for (const LayerDesc& l : layers_) {
+    switch (l.kind) {
+      case LayerKind::HeadConv: {
+        cur = act(R, R, l.cout);
+        const float* cond = cfg_.conditional ? ws.cond : nullptr;
+        const int cc = cfg_.conditional ? oc : 0;
+        const float *xw = ws.x, *hw = head_w_, *hb = T_(l.name + ".bias");
+        bf16* dst = cur.ptr;
+        const int co = l.cout;
+        ws.ops.push_back(Op{l.name, false, [=](cudaStream_t s) {
+          launch_head_conv(cond, xw, cc, oc, hw, hb, B, R, co, dst, s);
+        }});
+        feats.push_back(cur);
+        break;
+      }
+      case LayerKind::Down: {
+        const PackedConv& pc = convs_.at(l.name + ".conv");
+        cur = conv(l.name, cur, 9, 2, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H / 2, cur.W / 2);
+        feats.push_back(cur);
+        break;
+      }
+      case LayerKind::Up: {
+        const PackedConv& pc = convs_.at(l.name + ".conv");
+        Act up = act(cur.H * 2, cur.W * 2, cur.C);
+        const Act src = cur;
+        ws.ops.push_back(Op{l.name + ".upsample", false, [src, up](cudaStream_t s) {
+          launch_upsample2x(src.ptr, up.ptr, src.B, src.H, src.W, src.C, s);
+        }});
+        cur = conv(l.name, up, 9, 1, pc, nullptr, nullptr, pc.bias, 0, nullptr, up.H, up.W);
+        break;
+      }
+      case LayerKind::Res: {
+        const bool is_up = l.c_skip > 0;
+        Act skip;
+        if (is_up) {
+          REQUIRE(!feats.empty(), "internal: skip stack underflow");
+          skip = feats.back();
+          feats.pop_back();
+          REQUIRE(skip.C == l.c_skip && skip.H == cur.H, "internal: skip tensor mismatch");
+        }
+        REQUIRE(cur.C == l.c_x, "internal: channel plan mismatch");
+        const std::string rb = l.name + ".res_block";
+        const Act xin = cur;
+        Act xn = group_norm(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0", true);
+        const PackedConv& c1 = convs_.at(l.name + ".c1");
+        Act h = conv(l.name + ".conv1", xn, 9, 1, c1, nullptr, nullptr, table_ + noise_off_.at(l.name),
+                     noise_total_, nullptr, xin.H, xin.W);
+        Act hn = group_norm(l.name + ".block2", h, nullptr, rb + ".block2.block.0", true);
+        const PackedConv& c2 = convs_.at(l.name + ".c2");
+        const bool has_res = c2.c_res0 > 0;
+        cur = conv(l.name + ".conv2", hn, 9, 1, c2, has_res ? &xin : nullptr, (has_res && is_up) ? &skip : nullptr,
+                   c2.bias, 0, has_res ? nullptr : xin.ptr, xin.H, xin.W);
+        if (l.attn) {
+          const Act ain = cur;
+          Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);
+          Act qkv = conv(l.name + ".attn.qkv", an, 1, 1, convs_.at(l.name + ".qkv"), nullptr, nullptr, nullptr, 0,
+                         nullptr, ain.H, ain.W);
+          Act ao = act(ain.H, ain.W, ain.C);
+          ws.ops.push_back(Op{l.name + ".attn.core", false, [qkv, ao](cudaStream_t s) {
+            launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
+          }});
+          const PackedConv& po = convs_.at(l.name + ".out");
+          cur = conv(l.name + ".attn.out", ao, 1, 1, po, nullptr, nullptr, po.bias, 0, ain.ptr, ain.H, ain.W);
+        }
+        if (l.name.compare(0, 6, "downs.") == 0) feats.push_back(cur);
+        break;
+      }
+      case LayerKind::Final: {
+        Act fn = group_norm(l.name, cur, nullptr, l.name + ".block.0", true);
+        auto tp = std::make_shared<TailPlan>();
+        tp->src = fn.ptr; tp->w = tail_w_; tp->bias = T_(l.name + ".block.3.bias");
+        tp->B = B; tp->R = R; tp->C = fn.C; tp->OC = oc;
+        tp->eps_out = nullptr; tp->x = ws.x; tp->coefs = coefs_; tp->ctl = ctl_;
+        ws.tail_plan = tp;
+        ws.ops.push_back(Op{l.name + ".tail", false, [tp](cudaStream_t s) { launch_tail(*tp, s); }});
+        break;
+      }
+    }
+    if (l.kind != LayerKind::Final) ws.layer_out[l.name] = cur;
+  }
+}
+
+void Engine::write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, cudaStream_t s) {
+  StepCtl c;
+  c.t = t; c.T = T_sched_; c.noise_mode = mode; c.pad = 0;
+  c.noise = noise; c.seed = seed; c.numel = numel;
+  CUDA_CHECK(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, s));
+}
+
+void Engine::run_ops(Workspace& ws, cudaStream_t s) {
+  for (auto& op : ws.ops) op.run(s);
+  last_total += (int64_t)ws.ops.size();
+  last_conv += ws.n_conv;
+}
+
+void Engine::ensure_graph(Workspace& ws) {
+  if (ws.graph || !use_graph_) return;
+  // The tail must be in "update" mode while capturing (plans are read at launch = capture time).
+  ws.tail_plan->eps_out = nullptr;
+  ws.tail_plan->x = ws.x;
+  cudaGraph_t g = nullptr;
+  CUDA_CHECK(cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal));
+  try {
+    for (auto& op : ws.ops) op.run(capture_stream_);
+    launch_ctl_advance(ctl_, capture_stream_);
+  } catch (...) {
+    cudaStreamEndCapture(capture_stream_, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  CUDA_CHECK(cudaStreamEndCapture(capture_stream_, &g));
+  cudaError_t e = cudaGraphInstantiate(&ws.graph, g, 0);
+  cudaGraphDestroy(g);
+  CUDA_CHECK(e);
+}
+
+// ------------------------------------------------------------------------------- entry points
+void Engine::unet_forward(const float* cond, const float* x, float noise_level, int B, int R, float* eps,
+                          cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  Workspace& ws = workspace(B, R);
+  REQUIRE(x && eps, "unet_forward: null pointer");
+  REQUIRE(cond || !cfg_.conditional, "unet_forward: cond is required for a conditional model");
+  const size_t img = (size_t)B * cfg_.out_channel * R * R * sizeof(float);
+  last_total = last_conv = 0;
+  if (cond) CUDA_CHECK(cudaMemcpyAsync(ws.cond, cond, img, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(ws.x, x, img, cudaMemcpyDeviceToDevice, s));
+  // scratch row T of the bias table <- this noise level
+  CUDA_CHECK(cudaMemcpyAsync(nl_ + T_sched_, &noise_level, sizeof(float), cudaMemcpyHostToDevice, s));
+  NoiseTablePlan np{nl_, T_("noise_level_mlp.1.weight"), T_("noise_level_mlp.1.bias"),
+                    T_("noise_level_mlp.3.weight"), T_("noise_level_mlp.3.bias"), wall_, ball_,
+                    cfg_.inner_channel, noise_total_, table_};
+  launch_noise_table(np, T_sched_, 1, s);
+  write_ctl(T_sched_, 0, nullptr, 0, 0, s);
+  ws.tail_plan->eps_out = ws.eps;
+  ws.tail_plan->x = nullptr;
+  run_ops(ws, s);
+  ws.tail_plan->eps_out = nullptr;
+  ws.tail_plan->x = ws.x;
+  CUDA_CHECK(cudaMemcpyAsync(eps, ws.eps, img, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void Engine::step(const float* cond, const float* x_t, const float* noise, int t, int B, int R, float* x_tm1,
+                  cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  REQUIRE(T_sched_ > 0, "step: no noise schedule installed (call b200sr3_set_schedule)");
+  REQUIRE(t >= 0 && t < T_sched_, "step: t out of range");
+  Workspace& ws = workspace(B, R);
+  REQUIRE(x_t && x_tm1, "step: null pointer");
+  REQUIRE(cond || !cfg_.conditional, "step: cond is required for a conditional model");
+  const size_t img = (size_t)B * cfg_.out_channel * R * R * sizeof(float);
+  last_total = last_conv = 0;
+  if (cond) CUDA_CHECK(cudaMemcpyAsync(ws.cond, cond, img, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(ws.x, x_t, img, cudaMemcpyDeviceToDevice, s));
+  write_ctl(t, 3, noise, 0, (long long)(img / sizeof(float)), s);
+  ws.tail_plan->eps_out = nullptr;
+  ws.tail_plan->x = ws.x;
+  run_ops(ws, s);
+  CUDA_CHECK(cudaMemcpyAsync(x_tm1, ws.x, img, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void Engine::sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int B, int R,
+                    float* out, float* snapshots, cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  REQUIRE(T_sched_ > 0, "sample: no noise schedule installed (call b200sr3_set_schedule)");
+  REQUIRE(noise_mode == B200SR3_NOISE_INJECTED || noise_mode == B200SR3_NOISE_PHILOX, "sample: bad noise_mode");
+  REQUIRE(noise_mode != B200SR3_NOISE_INJECTED || noise != nullptr, "sample: injected mode needs a noise list");
+  REQUIRE(out != nullptr, "sample: null output");
+  REQUIRE(cond || !cfg_.conditional, "sample: cond is required for a conditional model");
+  Workspace& ws = workspace(B, R);
+  const int T = T_sched_;
+  const size_t numel = (size_t)B * cfg_.out_channel * R * R;
+  const size_t img = numel * sizeof(float);
+  last_total = last_conv = 0;
+  ensure_graph(ws);
+  if (cond) CUDA_CHECK(cudaMemcpyAsync(ws.cond, cond, img, cudaMemcpyDeviceToDevice, s));
+  // x_T (diffusion.py:205): first entry of the injected list, or a Philox draw keyed at t = T
+  if (noise_mode == B200SR3_NOISE_INJECTED) {
+    CUDA_CHECK(cudaMemcpyAsync(ws.x, noise, img, cudaMemcpyDeviceToDevice, s));
+  } else {
+    // same generator as the update kernel, keyed at t = T (never a real step)
+    launch_philox_fill(ws.x, B, cfg_.out_channel, R, seed, T, s);
+  }
+  write_ctl(T - 1, noise_mode, noise, seed, (long long)numel, s);
+  ws.tail_plan->eps_out = nullptr;
+  ws.tail_plan->x = ws.x;
+  const int inter = 1 | (T / 10);
+  int snap = 0;
+  for (int t = T - 1; t >= 0; --t) {
+    if (ws.graph) {
+      CUDA_CHECK(cudaGraphLaunch(ws.graph, s));
+      last_total += (int64_t)ws.ops.size() + 1;
+      last_conv += ws.n_conv;
+    } else {
+      run_ops(ws, s);
+      launch_ctl_advance(ctl_, s);
+      last_total += 1;
+    }
+    if (snapshots && t % inter == 0)
+      CUDA_CHECK(cudaMemcpyAsync(snapshots + (size_t)(snap++) * numel, ws.x, img, cudaMemcpyDeviceToDevice, s));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(out, ws.x, img, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void Engine::sample_host(const float* cond_host, uint64_t seed, int B, int R, float* out_host, cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  Workspace& ws = workspace(B, R);
+  const size_t img = (size_t)B * cfg_.out_channel * R * R * sizeof(float);
+  REQUIRE(out_host != nullptr, "sample_host: null output");
+  REQUIRE(cond_host || !cfg_.conditional, "sample_host: cond is required for a conditional model");
+  if (cond_host) CUDA_CHECK(cudaMemcpyAsync(ws.eps, cond_host, img, cudaMemcpyHostToDevice, s));
+  // ws.eps doubles as the staging buffer: sample() copies cond -> ws.cond and out <- ws.x
+  sample(cond_host ? ws.eps : nullptr, B200SR3_NOISE_PHILOX, nullptr, seed, B, R, ws.eps, nullptr, s);
+  CUDA_CHECK(cudaMemcpyAsync(out_host, ws.eps, img, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void Engine::layer_output(const std::string& layer, float* dst, int* C, int* H, int* W, cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  for (auto& kv : workspaces_) {
+    Workspace& ws = *kv.second;
+    auto it = ws.layer_out.find(layer);
+    if (it == ws.layer_out.end()) continue;
+    // the most recently used workspace is not tracked; with one live (B,R) this is unambiguous
+    const Act& a = it->second;
+    if (C) *C = a.C;
+    if (H) *H = a.H;
+    if (W) *W = a.W;
+    if (dst) {
+      launch_nhwc_to_nchw(a.ptr, dst, a.B, a.C, a.H, a.W, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    return;
+  }
+  throw Error("layer_output: no activation named '" + layer + "' (run a forward first)");
+}
+
+}  // namespace b200sr3

@@ -1,0 +1,144 @@
+// Host-side engine: layer plan of the reference UNet, packed weights, per-(B,R) workspace with
+// a static buffer plan, TMA descriptors and one CUDA graph per sampling step.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sr3.h"
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace b200sr3 {
+
+enum class LayerKind { HeadConv, Res, Down, Up, Final };
+
+struct LayerDesc {
+  std::string name;   // reference module path: "downs.3", "mid.0", "ups.18", "final_conv"
+  LayerKind kind;
+  int c_x = 0;        // channels arriving on the main path
+  int c_skip = 0;     // channels of the skip tensor concatenated after it (ups only)
+  int cout = 0;
+  bool attn = false;
+};
+
+struct TensorSpec {
+  std::string key;
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  bool loaded = false;
+  size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
+};
+
+struct PackedConv {     // weights of one tensor-core conv
+  bf16* w = nullptr;    // [Cout][k_total]
+  int cout = 0, k_total = 0;
+  int taps = 9;         // main segment: 9 or 1
+  int cin_main = 0;     // channels of the main source
+  int c_res0 = 0, c_res1 = 0;   // folded 1x1 res_conv segments (0 = none)
+  float* bias = nullptr;        // static bias [Cout] (null when the bias comes from the table)
+};
+
+// A launch that is part of the per-step kernel chain.
+struct Op {
+  std::string name;
+  bool is_conv = false;
+  std::function<void(cudaStream_t)> run;
+};
+
+class Engine;
+
+struct Workspace {
+  int B = 0, R = 0;
+  std::vector<void*> allocations;
+  size_t bytes = 0;
+  float* cond = nullptr;   // fp32 NCHW
+  float* x = nullptr;      // fp32 NCHW sampler state
+  float* eps = nullptr;    // fp32 NCHW (unet_forward output)
+  std::vector<Op> ops;     // one UNet forward + update, in order
+  TailPlan* tail = nullptr;   // points into the closure-owned plan of the last op
+  std::shared_ptr<TailPlan> tail_plan;
+  std::map<std::string, Act> layer_out;
+  cudaGraphExec_t graph = nullptr;
+  int64_t n_conv = 0;
+  ~Workspace();
+};
+
+class Engine {
+ public:
+  Engine(const b200sr3_config& cfg, int device);
+  ~Engine();
+
+  int num_tensors() const { return (int)tensors_.size(); }
+  const TensorSpec& tensor(int i) const { return tensors_.at(i); }
+  void load_tensor(const std::string& key, const float* data, const int64_t* shape, int ndim);
+  void finalize_weights(cudaStream_t s);
+  void set_schedule(int T, const float* a, const float* bc, const float* c1, const float* c2,
+                    const float* lv, const double* sqrt_ac_prev, cudaStream_t s);
+
+  void unet_forward(const float* cond, const float* x, float noise_level, int B, int R, float* eps,
+                    cudaStream_t s);
+  void step(const float* cond, const float* x_t, const float* noise, int t, int B, int R, float* x_tm1,
+            cudaStream_t s);
+  void sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int B, int R,
+              float* out, float* snapshots, cudaStream_t s);
+  void sample_host(const float* cond_host, uint64_t seed, int B, int R, float* out_host, cudaStream_t s);
+  int num_snapshots() const;
+  void layer_output(const std::string& layer, float* dst, int* C, int* H, int* W, cudaStream_t s);
+
+  int64_t last_total = 0, last_conv = 0;
+  int device() const { return device_; }
+
+ private:
+  friend struct Workspace;
+  void build_layers();
+  void add_tensor(const std::string& key, std::vector<int64_t> shape);
+  float* T_(const std::string& key) const;       // device pointer of a loaded tensor
+  Workspace& workspace(int B, int R);
+  void build_workspace(Workspace& ws);
+  void write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, cudaStream_t s);
+  void run_ops(Workspace& ws, cudaStream_t s);
+  void ensure_graph(Workspace& ws);
+
+  b200sr3_config cfg_;
+  int device_ = 0;
+  std::vector<LayerDesc> layers_;
+  std::vector<TensorSpec> tensors_;
+  std::map<std::string, int> tensor_index_;
+  bool finalized_ = false;
+
+  std::map<std::string, PackedConv> convs_;       // "<layer>.c1", ".c2", ".conv", ".qkv", ".out"
+  std::map<std::string, int> noise_off_;          // layer -> column offset in the bias table
+  int noise_total_ = 0;
+  float *head_w_ = nullptr, *tail_w_ = nullptr;
+  float *wall_ = nullptr, *ball_ = nullptr;
+  std::vector<void*> owned_;
+
+  int T_sched_ = 0;
+  float* coefs_ = nullptr;   // [5][T]
+  float* nl_ = nullptr;      // [T+1]
+  float* table_ = nullptr;   // [T+1][noise_total]
+  StepCtl* ctl_ = nullptr;
+  cudaStream_t capture_stream_ = nullptr;
+  bool use_graph_ = true;
+  int force_block_n_ = 0;
+
+  std::map<std::pair<int, int>, std::unique_ptr<Workspace>> workspaces_;
+};
+
+// Builds the launch closure of one tensor-core convolution (conv_umma.cu).
+struct ConvSource {
+  Act act;            // source activation
+  int taps = 9;       // 9: 3x3 pad 1; 1: 1x1
+  int stride = 1;     // 1 or 2 (main source only)
+};
+Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0, const Act* res1,
+                const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl,
+                const bf16* residual, const Act& out, int force_block_n);
+// Shared-memory opt-in for every conv kernel instance (once per process / device).
+void conv_init_device();
+
+}  // namespace b200sr3

@@ -1,0 +1,621 @@
+// Non-GEMM kernels of the SR3 sampling step: GroupNorm(+Swish), head conv, tail conv fused with
+// the posterior update, mid-block attention core, nearest upsample, weight packing and the
+// noise-embedding bias table. HBM-bound kernels use 16-byte vector accesses on NHWC bf16.
+#include "kernels.cuh"
+
+namespace b200sr3 {
+
+// =============================================================================== GroupNorm
+// Pass 1: per-CTA partial (sum, sumsq) per channel; the last CTA of an image (ticket) reduces
+// the partials in a fixed order (deterministic), forms the group statistics and writes the
+// per-(image, channel) scale/shift that pass 2 (or a fused consumer) applies.
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
+  __shared__ float red[256 * 16];
+  __shared__ float chan[2048 * 2];
+  __shared__ float gstat[64 * 2];
+  __shared__ int is_last;
+  const int C = g.C0 + g.C1;
+  const int Cv = C >> 3;
+  const int rows = 256 / Cv;
+  const int tid = threadIdx.x;
+  const int cv = tid % Cv, r = tid / Cv;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int ppc = (g.HW + g.chunks - 1) / g.chunks;
+  const int p_begin = chunk * ppc;
+  const int p_end = min(g.HW, p_begin + ppc);
+
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < rows) {
+    const int c = cv * 8;
+    const bf16* base;
+    int cs;
+    if (c < g.C0) { base = g.src0 + c; cs = g.C0; } else { base = g.src1 + (c - g.C0); cs = g.C1; }
+    base += (size_t)b * g.HW * cs;
+    for (int p = p_begin + r; p < p_end; p += rows) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs));
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[tid * 16 + i] = s[i]; red[tid * 16 + 8 + i] = q[i]; }
+  __syncthreads();
+  if (r == 0) {
+    float* dst = g.partial + ((size_t)(b * g.chunks + chunk) * C + cv * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f, d = 0.f;
+      for (int rr = 0; rr < rows; ++rr) { a += red[(rr * Cv + cv) * 16 + i]; d += red[(rr * Cv + cv) * 16 + 8 + i]; }
+      dst[2 * i] = a;
+      dst[2 * i + 1] = d;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(&g.ticket[b], 1) == g.chunks - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = tid; c < C; c += 256) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < g.chunks; ++k) {
+      const float2 v = *reinterpret_cast<const float2*>(g.partial + ((size_t)(b * g.chunks + k) * C + c) * 2);
+      a += v.x;
+      d += v.y;
+    }
+    chan[2 * c] = a;
+    chan[2 * c + 1] = d;
+  }
+  __syncthreads();
+  const int cg = C / g.groups;
+  if (tid < g.groups) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cg; ++k) { a += chan[2 * (tid * cg + k)]; d += chan[2 * (tid * cg + k) + 1]; }
+    const float inv_n = 1.0f / ((float)g.HW * (float)cg);
+    const float mean = a * inv_n;
+    const float var = fmaxf(d * inv_n - mean * mean, 0.f);
+    gstat[2 * tid] = mean;
+    gstat[2 * tid + 1] = rsqrtf(var + 1e-5f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    const int grp = c / cg;
+    const float sc = gstat[2 * grp + 1] * g.gamma[c];
+    float2 o;
+    o.x = sc;
+    o.y = g.beta[c] - gstat[2 * grp] * sc;
+    *reinterpret_cast<float2*>(g.scale_shift + ((size_t)b * C + c) * 2) = o;
+  }
+  if (tid == 0) g.ticket[b] = 0;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnPlan g) {
+  const int C = g.C0 + g.C1;
+  const int Cv = C >> 3;
+  const long long total = (long long)g.B * g.HW * Cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % Cv);
+    const long long bp = idx / Cv;           // b*HW + p
+    const int b = (int)(bp / g.HW);
+    const int c = cv * 8;
+    const bf16* src = (c < g.C0) ? g.src0 + bp * g.C0 + c : g.src1 + bp * g.C1 + (c - g.C0);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+    float f[8];
+    unpack8(v, f);
+    const float4* ss = reinterpret_cast<const float4*>(g.scale_shift + ((size_t)b * C + c) * 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(ss + i);        // (scale, shift) x 2 channels
+      float y0 = fmaf(f[2 * i], t.x, t.y);
+      float y1 = fmaf(f[2 * i + 1], t.z, t.w);
+      if (g.swish) { y0 = swish_f(y0); y1 = swish_f(y1); }
+      f[2 * i] = y0;
+      f[2 * i + 1] = y1;
+    }
+    *reinterpret_cast<uint4*>(g.dst + bp * C + c) = pack8(f);
+  }
+}
+
+void gn_choose_chunks(GnPlan& g) {
+  const int C = g.C0 + g.C1;
+  long long per_img = (long long)g.HW * C;
+  long long ch = per_img / (256LL * 8 * 8);
+  if (ch < 1) ch = 1;
+  if (ch > 64) ch = 64;
+  if (ch > g.HW) ch = g.HW;
+  g.chunks = (int)ch;
+}
+
+void launch_gn_stats(const GnPlan& g, cudaStream_t s) {
+  const int C = g.C0 + g.C1;
+  REQUIRE(C % 8 == 0 && g.C0 % 8 == 0 && C <= 2048 && C % g.groups == 0 && g.groups <= 64,
+          "GroupNorm: unsupported channel count");
+  gn_stats_kernel<<<dim3(g.chunks, g.B), 256, 0, s>>>(g);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gn_apply(const GnPlan& g, cudaStream_t s) {
+  const long long total = (long long)g.B * g.HW * ((g.C0 + g.C1) >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  gn_apply_kernel<<<(int)blocks, 256, 0, s>>>(g);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== head conv
+// 3x3, pad 1, Cin = c_cond + c_x (6) read straight from the fp32 NCHW sampler state, so x_t is
+// never rounded to bf16 on the way in. K = 54: CUDA cores.
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ cond,
+                                                        const float* __restrict__ x, int c_cond, int c_x,
+                                                        const float* __restrict__ w_kc,
+                                                        const float* __restrict__ bias, int B, int R,
+                                                        int Cout, bf16* __restrict__ out) {
+  extern __shared__ float w_s[];   // [K][Cout]
+  const int Cin = c_cond + c_x;
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) w_s[i] = w_kc[i];
+  __syncthreads();
+  const int tpp = Cout >> 3;                     // threads per pixel
+  const int ppb = blockDim.x / tpp;              // pixels per block
+  const int cgp = threadIdx.x % tpp;
+  const long long pix = (long long)blockIdx.x * ppb + threadIdx.x / tpp;
+  const long long npix = (long long)B * R * R;
+  if (pix >= npix || threadIdx.x / tpp >= ppb) return;
+  const int xw = (int)(pix % R);
+  const int yh = (int)((pix / R) % R);
+  const int b = (int)(pix / ((long long)R * R));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = bias[cgp * 8 + i];
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+    if (yy < 0 || yy >= R || xx < 0 || xx >= R) continue;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = (ci < c_cond) ? __ldg(cond + (((size_t)b * c_cond + ci) * R + yy) * R + xx)
+                                    : __ldg(x + (((size_t)b * c_x + (ci - c_cond)) * R + yy) * R + xx);
+      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * Cin + ci) * Cout + cgp * 8);
+      const float4 w0 = wr[0], w1 = wr[1];
+      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+      acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+      acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + pix * Cout + cgp * 8) = pack8(acc);
+}
+
+void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
+                      const float* bias, int B, int R, int Cout, bf16* out, cudaStream_t s) {
+  REQUIRE(Cout % 8 == 0 && Cout <= 2048, "head conv: Cout must be a multiple of 8");
+  const int tpp = Cout / 8;
+  const int threads = 256 / tpp * tpp > 0 ? (256 / tpp) * tpp : tpp;
+  const int ppb = threads / tpp;
+  const long long npix = (long long)B * R * R;
+  const size_t smem = (size_t)(c_cond + c_x) * 9 * Cout * sizeof(float);
+  REQUIRE(smem <= 48 * 1024, "head conv: weights exceed 48 KB of shared memory");
+  head_conv_kernel<<<(unsigned)((npix + ppb - 1) / ppb), threads, smem, s>>>(cond, x, c_cond, c_x, w_kc, bias,
+                                                                            B, R, Cout, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== philox
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// =============================================================================== tail + update
+// One thread per pixel: eps[oc] = bias[oc] + sum_{tap,c} src[pix+tap][c] * w[oc][tap][c]
+// then the reference's update, op for op (diffusion.py:150-151, 175-176, 159-160, 186-187).
+__device__ __forceinline__ float posterior_update(float x, float eps, float z, float a, float bc,
+                                                  float c1, float c2, float sigma) {
+  float x0 = __fsub_rn(__fmul_rn(a, x), __fmul_rn(bc, eps));
+  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
+  return __fadd_rn(mean, __fmul_rn(z, sigma));
+}
+
+template <int OC>
+__global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
+  extern __shared__ float w_s[];   // [OC][9][C]
+  const int C = t.C, R = t.R;
+  for (int i = threadIdx.x; i < OC * 9 * C; i += blockDim.x) w_s[i] = t.w[i];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)t.B * R * R;
+  if (pix >= npix) return;
+  const int xw = (int)(pix % R);
+  const int yh = (int)((pix / R) % R);
+  const int b = (int)(pix / ((long long)R * R));
+  float acc[OC];
+#pragma unroll
+  for (int o = 0; o < OC; ++o) acc[o] = t.bias[o];
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+    if (yy < 0 || yy >= R || xx < 0 || xx >= R) continue;
+    const bf16* src = t.src + (((size_t)b * R + yy) * R + xx) * C;
+    for (int c = 0; c < C; c += 8) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + c)), f);
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {
+        const float4* wr = reinterpret_cast<const float4*>(w_s + (o * 9 + tap) * C + c);
+        const float4 w0 = wr[0], w1 = wr[1];
+        acc[o] = fmaf(f[0], w0.x, acc[o]); acc[o] = fmaf(f[1], w0.y, acc[o]);
+        acc[o] = fmaf(f[2], w0.z, acc[o]); acc[o] = fmaf(f[3], w0.w, acc[o]);
+        acc[o] = fmaf(f[4], w1.x, acc[o]); acc[o] = fmaf(f[5], w1.y, acc[o]);
+        acc[o] = fmaf(f[6], w1.z, acc[o]); acc[o] = fmaf(f[7], w1.w, acc[o]);
+      }
+    }
+  }
+  const size_t plane = (size_t)R * R;
+  const size_t base = (size_t)b * OC * plane + (size_t)yh * R + xw;
+  if (t.eps_out) {
+#pragma unroll
+    for (int o = 0; o < OC; ++o) t.eps_out[base + o * plane] = acc[o];
+  }
+  if (t.x == nullptr) return;
+  const int ts = t.ctl->t, T = t.ctl->T;
+  const float a = t.coefs[ts], bc = t.coefs[T + ts], c1 = t.coefs[2 * T + ts], c2 = t.coefs[3 * T + ts];
+  const float sigma = expf(0.5f * t.coefs[4 * T + ts]);
+  float z[OC];
+#pragma unroll
+  for (int o = 0; o < OC; ++o) z[o] = 0.f;
+  const int mode = t.ctl->noise_mode;
+  if (ts > 0) {
+    if (mode == 1 || mode == 3) {
+      const float* zp = t.ctl->noise;
+      if (zp) {
+        if (mode == 1) zp += (size_t)(T - ts) * (size_t)t.ctl->numel;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) z[o] = __ldg(zp + base + o * plane);
+      }
+    } else if (mode == 2) {
+      const unsigned long long seed = t.ctl->seed;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+      const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
+#pragma unroll
+      for (int o = 0; o < OC; ++o) z[o] = zz[o & 3];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < OC; ++o) {
+    const float xv = t.x[base + o * plane];
+    t.x[base + o * plane] = posterior_update(xv, acc[o], z[o], a, bc, c1, c2, sigma);
+  }
+}
+
+void launch_tail(const TailPlan& t, cudaStream_t s) {
+  REQUIRE(t.C % 8 == 0, "tail conv: C must be a multiple of 8");
+  const long long npix = (long long)t.B * t.R * t.R;
+  const size_t smem = (size_t)t.OC * 9 * t.C * sizeof(float);
+  REQUIRE(smem <= 48 * 1024, "tail conv: weights exceed 48 KB of shared memory");
+  const unsigned blocks = (unsigned)((npix + 127) / 128);
+  switch (t.OC) {
+    case 1: tail_kernel<1><<<blocks, 128, smem, s>>>(t); break;
+    case 3: tail_kernel<3><<<blocks, 128, smem, s>>>(t); break;
+    case 4: tail_kernel<4><<<blocks, 128, smem, s>>>(t); break;
+    default: throw Error("tail conv: out_channel must be 1, 3 or 4");
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void philox_fill_kernel(float* x, int B, int C, int R, unsigned long long seed, int t) {
+  const long long npix = (long long)B * R * R;
+  const size_t plane = (size_t)R * R;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)t, 0x5352u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+    const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
+    const int b = (int)(pix / plane);
+    const size_t base = (size_t)b * C * plane + (size_t)(pix % plane);
+    for (int c = 0; c < C; ++c) x[base + c * plane] = zz[c & 3];
+  }
+}
+void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, cudaStream_t s) {
+  const long long npix = (long long)B * R * R;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  philox_fill_kernel<<<(int)blocks, 256, 0, s>>>(x, B, C, R, seed, t);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void ctl_advance_kernel(StepCtl* ctl) { ctl->t -= 1; }
+void launch_ctl_advance(StepCtl* ctl, cudaStream_t s) {
+  ctl_advance_kernel<<<1, 1, 0, s>>>(ctl);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void posterior_update_kernel(const float* x, const float* eps, const float* z, float a, float b,
+                                        float c1, float c2, float logvar, long long n, float* out) {
+  const float sigma = expf(0.5f * logvar);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = posterior_update(x[i], eps[i], z ? z[i] : 0.f, a, b, c1, c2, sigma);
+}
+void launch_posterior_update(const float* x, const float* eps, const float* z, float a, float b, float c1,
+                             float c2, float logvar, long long n, float* out, cudaStream_t s) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  posterior_update_kernel<<<(int)blocks, 256, 0, s>>>(x, eps, z, a, b, c1, c2, logvar, n, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== attention
+// One warp per query token. qkv is the 1x1 conv output [B, HW, 3C] (q | k | v along channels,
+// unet.py:128-129). Scores and softmax in fp32; HW <= 64 tokens for every shipped config.
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_MAXV = 4;   // C <= 1024
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* __restrict__ qkv,
+                                                                   bf16* __restrict__ out, int HW, int C) {
+  extern __shared__ float sc_s[];   // [ATT_WARPS][HW]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int qi = blockIdx.x * ATT_WARPS + warp;
+  if (qi >= HW) return;
+  float* sc = sc_s + warp * HW;
+  const int Cv = C >> 3;
+  const size_t row = (size_t)3 * C;
+  const bf16* base = qkv + (size_t)b * HW * row;
+  float q[ATT_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < ATT_MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < Cv) unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)qi * row + v * 8)), q[i]);
+  }
+  const float scale = rsqrtf((float)C);
+  float mx = -INFINITY;
+  for (int j = 0; j < HW; ++j) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < Cv) {
+        float k[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)j * row + C + v * 8)), k);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(q[i][e], k[e], d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    d *= scale;
+    if (lane == 0) sc[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < HW; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  float acc[ATT_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < ATT_MAXV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  for (int j = 0; j < HW; ++j) {
+    const float pj = sc[j];
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < Cv) {
+        float vv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)j * row + 2 * C + v * 8)), vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(pj, vv[e], acc[i][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ATT_MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < Cv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[i][e] *= inv;
+      *reinterpret_cast<uint4*>(out + ((size_t)b * HW + qi) * C + v * 8) = pack8(acc[i]);
+    }
+  }
+}
+
+void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStream_t s) {
+  REQUIRE(C % 8 == 0 && C <= 1024, "attention: C must be a multiple of 8 and <= 1024");
+  const size_t smem = (size_t)ATT_WARPS * HW * sizeof(float);
+  REQUIRE(smem <= 160 * 1024, "attention: too many tokens");
+  if (smem > 48 * 1024)
+    CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_kernel<<<dim3(ceil_div(HW, ATT_WARPS), B), ATT_WARPS * 32, smem, s>>>(qkv, out, HW, C);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== upsample
+__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst,
+                                                         int B, int H, int W, int Cv) {
+  const long long total = (long long)B * 4 * H * W * Cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % Cv);
+    long long p = idx / Cv;
+    const int xo = (int)(p % (2 * W)); p /= 2 * W;
+    const int yo = (int)(p % (2 * H));
+    const int b = (int)(p / (2 * H));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + (((size_t)b * H + (yo >> 1)) * W + (xo >> 1)) * Cv + cv);
+    reinterpret_cast<uint4*>(dst)[idx] = v;
+  }
+}
+void launch_upsample2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cudaStream_t s) {
+  REQUIRE(C % 8 == 0, "upsample: C must be a multiple of 8");
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  upsample2x_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, B, H, W, C / 8);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== weight packing
+__global__ void pack_conv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin,
+                                        int taps, int cin_pad, int k_off, int k_total) {
+  const long long total = (long long)Cout * taps * cin_pad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cin_pad);
+    const int tap = (int)((idx / cin_pad) % taps);
+    const int o = (int)(idx / ((long long)cin_pad * taps));
+    const float v = (c < Cin) ? src[((size_t)o * Cin + c) * taps + tap] : 0.f;
+    dst[(size_t)o * k_total + k_off + tap * cin_pad + c] = __float2bfloat16_rn(v);
+  }
+}
+void launch_pack_conv_weight(const float* src, bf16* dst, int Cout, int Cin, int taps, int cin_pad, int k_off,
+                             int k_total, cudaStream_t s) {
+  const long long total = (long long)Cout * taps * cin_pad;
+  pack_conv_weight_kernel<<<(int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, s>>>(
+      src, dst, Cout, Cin, taps, cin_pad, k_off, k_total);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void pack_head_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin) {
+  const int total = Cout * Cin * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int o = idx % Cout;
+    const int ci = (idx / Cout) % Cin;
+    const int tap = idx / (Cout * Cin);
+    dst[idx] = src[((size_t)o * Cin + ci) * 9 + tap];   // dst[(tap*Cin+ci)*Cout + o]
+  }
+}
+void launch_pack_head_weight(const float* src, float* dst, int Cout, int Cin, cudaStream_t s) {
+  pack_head_weight_kernel<<<ceil_div(Cout * Cin * 9, 256), 256, 0, s>>>(src, dst, Cout, Cin);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void pack_tail_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int OC, int Cin) {
+  const int total = OC * 9 * Cin;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % Cin;
+    const int tap = (idx / Cin) % 9;
+    const int o = idx / (Cin * 9);
+    dst[idx] = src[((size_t)o * Cin + c) * 9 + tap];    // dst[(o*9+tap)*Cin + c]
+  }
+}
+void launch_pack_tail_weight(const float* src, float* dst, int OC, int Cin, cudaStream_t s) {
+  pack_tail_weight_kernel<<<ceil_div(OC * Cin * 9, 256), 256, 0, s>>>(src, dst, OC, Cin);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== noise table
+__global__ void __launch_bounds__(256) noise_table_kernel(NoiseTablePlan p, int row0) {
+  extern __shared__ float sm[];   // pe[inner] | h[4*inner] | e[inner]
+  const int inner = p.inner, hid = 4 * inner, count = inner / 2;
+  float* pe = sm;
+  float* h = sm + inner;
+  float* e = h + hid;
+  const int row = row0 + blockIdx.x;
+  const float nl = p.nl[row];
+  for (int j = threadIdx.x; j < count; j += blockDim.x) {
+    const float step = (float)j / (float)count;
+    const float enc = nl * expf(-9.210340371976184f * step);
+    pe[j] = sinf(enc);
+    pe[count + j] = cosf(enc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hid; i += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < inner; ++j) a = fmaf(p.w1[i * inner + j], pe[j], a);
+    a += p.b1[i];
+    h[i] = a / (1.0f + expf(-a));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < hid; ++j) a = fmaf(p.w3[i * hid + j], h[j], a);
+    e[i] = a + p.b3[i];
+  }
+  __syncthreads();
+  float* dst = p.table + (size_t)row * p.total;
+  for (int n = threadIdx.x; n < p.total; n += blockDim.x) {
+    float a = 0.f;
+    const float* wr = p.wall + (size_t)n * inner;
+    for (int j = 0; j < inner; ++j) a = fmaf(wr[j], e[j], a);
+    dst[n] = a + p.ball[n];
+  }
+}
+void launch_noise_table(const NoiseTablePlan& p, int row0, int rows, cudaStream_t s) {
+  if (rows <= 0) return;
+  noise_table_kernel<<<rows, 256, 6 * p.inner * sizeof(float), s>>>(p, row0);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================== layout helpers
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, int C, int H, int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long p = idx / C;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    dst[idx] = __float2bfloat16_rn(src[(((size_t)b * C + c) * H + y) * W + x]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    long long p = idx / W;
+    const int y = (int)(p % H); p /= H;
+    const int c = (int)(p % C);
+    const int b = (int)(p / C);
+    dst[idx] = __bfloat162float(src[(((size_t)b * H + y) * W + x) * C + c]);
+  }
+}
+static int grid_for(long long total) {
+  long long blocks = (total + 255) / 256;
+  return (int)(blocks > 148LL * 32 ? 148LL * 32 : (blocks < 1 ? 1 : blocks));
+}
+void launch_nchw_to_nhwc(const float* src, bf16* dst, int B, int C, int H, int W, cudaStream_t s) {
+  nchw_to_nhwc_kernel<<<grid_for((long long)B * C * H * W), 256, 0, s>>>(src, dst, B, C, H, W);
+  CUDA_CHECK(cudaGetLastError());
+}
+void launch_nhwc_to_nchw(const bf16* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  nhwc_to_nchw_kernel<<<grid_for((long long)B * C * H * W), 256, 0, s>>>(src, dst, B, C, H, W);
+  CUDA_CHECK(cudaGetLastError());
+}
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_f32(float* p, float v, long long n, cudaStream_t s) {
+  fill_f32_kernel<<<grid_for(n), 256, 0, s>>>(p, v, n);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200sr3

@@ -1,0 +1,87 @@
+// Launchers of the non-GEMM kernels (definitions in kernels.cu). All activations are NHWC bf16;
+// the sampler state (x_t, cond, noise, eps) is fp32 NCHW as at the reference boundary.
+#pragma once
+#include "common.cuh"
+
+namespace b200sr3 {
+
+// ---- GroupNorm (unet.py:84, 117): statistics, then y = [swish]((x - mean) * rstd * gamma + beta)
+// The input may be the channel concat of two tensors (unet.py:261 feeds cat((x, skip), 1) to the
+// block); groups may straddle the seam, so statistics are taken per channel and grouped after.
+struct GnPlan {
+  const bf16* src0 = nullptr;   // [B,H,W,C0]
+  const bf16* src1 = nullptr;   // [B,H,W,C1] or null
+  int B = 0, HW = 0, C0 = 0, C1 = 0, groups = 32;
+  const float* gamma = nullptr;  // [C0+C1]
+  const float* beta = nullptr;
+  int chunks = 1;                // CTAs per image in the statistics pass
+  float* partial = nullptr;      // [B][chunks][C][2]
+  float* scale_shift = nullptr;  // [B][C][2]: y = x*scale + shift
+  int* ticket = nullptr;         // [B], zero on entry, self-resetting
+  bf16* dst = nullptr;           // [B,H,W,C0+C1]
+  int swish = 1;
+};
+void gn_choose_chunks(GnPlan& g);
+void launch_gn_stats(const GnPlan& g, cudaStream_t s);
+void launch_gn_apply(const GnPlan& g, cudaStream_t s);
+
+// ---- head conv (unet.py:196-197, downs.0): fp32 NCHW cond/x -> 3x3 conv -> NHWC bf16
+void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
+                      const float* bias, int B, int R, int Cout, bf16* out, cudaStream_t s);
+
+// ---- tail (unet.py:233 final conv on the normalised tensor) fused with the posterior update
+// (diffusion.py:144-187): eps = conv3x3(src) ; x0 = clamp(A x - B eps) ; x' = c1 x0 + c2 x + sigma z
+struct TailPlan {
+  const bf16* src = nullptr;   // GN+Swish output [B,R,R,C]
+  const float* w = nullptr;    // [OC][9][C] fp32
+  const float* bias = nullptr; // [OC]
+  int B = 0, R = 0, C = 0, OC = 3;
+  float* eps_out = nullptr;    // optional fp32 NCHW [B,OC,R,R]
+  float* x = nullptr;          // fp32 NCHW state, updated in place (null: eps only)
+  const float* coefs = nullptr;   // [5][T]: A, Bc, C1, C2, LV
+  const StepCtl* ctl = nullptr;
+};
+void launch_tail(const TailPlan& t, cudaStream_t s);
+void launch_ctl_advance(StepCtl* ctl, cudaStream_t s);
+// x[b][c][y][x] = N(0,1) from the same Philox stream the update kernel uses, keyed at step t
+void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, cudaStream_t s);
+
+// ---- standalone posterior update (kernel-level parity of diffusion.py:144-187 given eps)
+void launch_posterior_update(const float* x, const float* eps, const float* z, float a, float b,
+                             float c1, float c2, float logvar, long long n, float* out, cudaStream_t s);
+
+// ---- mid-block attention core (unet.py:123-139): softmax(Q K^T / sqrt(C)) V over HW tokens
+void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStream_t s);
+
+// ---- nearest 2x upsample (unet.py:61, nn.Upsample) NHWC
+void launch_upsample2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cudaStream_t s);
+
+// ---- weights / tables
+// OIHW fp32 -> dst[o][k_off + tap*cin_pad + c] bf16 (zero padded to cin_pad)
+void launch_pack_conv_weight(const float* src, bf16* dst, int Cout, int Cin, int taps, int cin_pad,
+                             int k_off, int k_total, cudaStream_t s);
+// OIHW fp32 -> [tap*Cin + c][o] fp32 (head) / [o][tap][c] fp32 (tail)
+void launch_pack_head_weight(const float* src, float* dst, int Cout, int Cin, cudaStream_t s);
+void launch_pack_tail_weight(const float* src, float* dst, int OC, int Cin, cudaStream_t s);
+
+// Noise-embedding bias table (unet.py:18-31 PositionalEncoding, 179-184 noise_level_mlp,
+// 34-50 FeatureWiseAffine): row r = Wall * mlp(pe(nl[r])) + ball for r in [row0, row0+rows).
+struct NoiseTablePlan {
+  const float* nl = nullptr;    // [rows_total] noise level per row
+  const float* w1 = nullptr;    // [4*inner][inner]
+  const float* b1 = nullptr;
+  const float* w3 = nullptr;    // [inner][4*inner]
+  const float* b3 = nullptr;
+  const float* wall = nullptr;  // [total][inner]
+  const float* ball = nullptr;  // [total]
+  int inner = 64, total = 0;
+  float* table = nullptr;       // [rows_total][total]
+};
+void launch_noise_table(const NoiseTablePlan& p, int row0, int rows, cudaStream_t s);
+
+// ---- layout conversion (tests / introspection only)
+void launch_nchw_to_nhwc(const float* src, bf16* dst, int B, int C, int H, int W, cudaStream_t s);
+void launch_nhwc_to_nchw(const bf16* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+void launch_fill_f32(float* p, float v, long long n, cudaStream_t s);
+
+}  // namespace b200sr3

@@ -1,0 +1,143 @@
+/*
+ * b200sr3 — C ABI of the B200 (sm_100a) SR3 reverse-diffusion sampler.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * zouiner/3d-super-resolution-Face-reconstruction: GaussianDiffusion.super_resolution /
+ * p_sample_loop driving the model/sr UNet denoiser. The reference has no FFI of its own (it is
+ * pure PyTorch), so every entry point below names the reference Python interface it replaces
+ * (paths relative to the reference root). Host code (Python, via ctypes) owns all tensors; the
+ * library owns only its packed weights, tables and per-(B,R) workspace.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b200sr3_last_error() then
+ *     returns a thread-local, NUL-terminated description.
+ *   - "device pointer" = CUDA global memory on the handle's device (torch: tensor.data_ptr()).
+ *   - images are fp32, NCHW, contiguous, range [-1, 1], exactly as the reference passes them.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - no function falls back to the CPU; without a usable sm_100 device create() fails.
+ */
+#ifndef B200SR3_H_
+#define B200SR3_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200SR3_API __attribute__((visibility("default")))
+#else
+#define B200SR3_API
+#endif
+
+#define B200SR3_ABI_VERSION 1
+#define B200SR3_MAX_LEVELS 8
+
+typedef struct b200sr3_handle b200sr3_handle;
+
+/* The keys define_G reads from opt['sr']['model'] (model/sr/networks.py:83-101). */
+typedef struct b200sr3_config {
+  int32_t in_channel;                         /* unet.in_channel  (6 = cond 3 + x 3)            */
+  int32_t out_channel;                        /* unet.out_channel (3)                           */
+  int32_t inner_channel;                      /* unet.inner_channel (64)                        */
+  int32_t norm_groups;                        /* unet.norm_groups, 32 when absent (networks.py:89-90) */
+  int32_t res_blocks;                         /* unet.res_blocks (2)                            */
+  int32_t n_mults;                            /* len(unet.channel_multiplier)                   */
+  int32_t channel_mults[B200SR3_MAX_LEVELS];  /* unet.channel_multiplier ([1,2,4,8,8])          */
+  int32_t n_attn_res;
+  int32_t attn_res[B200SR3_MAX_LEVELS];       /* unet.attn_res ([16])                           */
+  int32_t image_size;                         /* diffusion.image_size: only places attention
+                                                 (model/sr/sr3_modules/unet.py:192-197,211-220) */
+  int32_t conditional;                        /* diffusion.conditional                          */
+} b200sr3_config;
+
+/* Noise source of one sampling call (diffusion.py:186,205 draw from torch's global RNG). */
+enum {
+  B200SR3_NOISE_INJECTED = 1, /* caller supplies [x_T, z_{T-1}, ..., z_1]: T tensors of B*3*R*R */
+  B200SR3_NOISE_PHILOX = 2    /* in-kernel Philox4x32-10 keyed by (seed, t, element)            */
+};
+
+B200SR3_API const char* b200sr3_last_error(void);
+B200SR3_API int b200sr3_abi_version(void);
+
+/* Replaces unet.UNet(...) + diffusion.GaussianDiffusion(...) construction inside
+ * define_G (model/sr/networks.py:91-109). Fails if `device` is not compute capability 10.x. */
+B200SR3_API int b200sr3_create(const b200sr3_config* cfg, int device, b200sr3_handle** out);
+B200SR3_API int b200sr3_destroy(b200sr3_handle* h);
+
+/* Weight ingestion: replaces netG.load_state_dict (lib/trainer_temp.py:172-216,
+ * model/sr/model.py:164-195). `key` is the reference state_dict key WITHOUT the
+ * "denoise_fn." prefix (e.g. "downs.1.res_block.block1.block.3.weight"); `data` is fp32,
+ * host or device, in the reference's layout (conv OIHW, linear [out,in]). The expected key
+ * set can be enumerated with b200sr3_num_tensors / b200sr3_tensor_info. */
+B200SR3_API int b200sr3_num_tensors(b200sr3_handle* h);
+B200SR3_API int b200sr3_tensor_info(b200sr3_handle* h, int index, const char** key, int64_t shape[4], int* ndim);
+B200SR3_API int b200sr3_load_tensor(b200sr3_handle* h, const char* key, const float* data,
+                        const int64_t* shape, int ndim);
+/* Repack to the device layout (bf16, [Cout][tap][Cin] K-major; 1x1 res_conv appended as extra
+ * K columns of block2's conv) and build the noise-embedding weight matrix. Fails if a tensor
+ * is missing. */
+B200SR3_API int b200sr3_finalize_weights(b200sr3_handle* h, void* stream);
+
+/* Replaces GaussianDiffusion.set_new_noise_schedule (diffusion.py:93-142). The caller computes
+ * the float64 tables exactly as the reference does and passes HOST arrays:
+ * sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1/2,
+ * posterior_log_variance_clipped (fp32[T]) and sqrt_alphas_cumprod_prev (float64[T+1]).
+ * Builds the per-timestep noise-embedding bias table (unet.py:18-50,179-184) on the device. */
+B200SR3_API int b200sr3_set_schedule(b200sr3_handle* h, int T, const float* sqrt_recip_ac,
+                         const float* sqrt_recipm1_ac, const float* coef1, const float* coef2,
+                         const float* post_logvar, const double* sqrt_ac_prev, void* stream);
+
+/* Replaces UNet.forward(cat([cond, x], 1), noise_level) (unet.py:235-265, called at
+ * diffusion.py:170) with one scalar noise level for the whole batch. Device pointers;
+ * eps is fp32 [B, out_channel, R, R]. cond may be NULL when !conditional. */
+B200SR3_API int b200sr3_unet_forward(b200sr3_handle* h, const float* cond, const float* x, float noise_level,
+                         int B, int R, float* eps, void* stream);
+
+/* Replaces GaussianDiffusion.p_sample(x, t, condition_x=cond) (diffusion.py:182-187) with
+ * the step's noise given (teacher-forced parity). `noise` may be NULL (treated as zeros; it is
+ * ignored at t == 0 as in the reference). Device pointers. */
+B200SR3_API int b200sr3_step(b200sr3_handle* h, const float* cond, const float* x_t, const float* noise,
+                 int t, int B, int R, float* x_tm1, void* stream);
+
+/* Replaces GaussianDiffusion.p_sample_loop / super_resolution (diffusion.py:189-225), all T
+ * steps, batched. out: fp32 [B,3,R,R] = x after t = 0. snapshots (optional): fp32
+ * [n_snap,B,3,R,R], x after every t with t % (1 | T/10) == 0 in visiting order, which is what
+ * `continous=True` concatenates after cond. noise_mode INJECTED reads `noise` (T*B*3*R*R
+ * floats); PHILOX ignores it and uses `seed`. Device pointers. */
+B200SR3_API int b200sr3_sample(b200sr3_handle* h, const float* cond, int noise_mode, const float* noise,
+                   uint64_t seed, int B, int R, float* out, float* snapshots, void* stream);
+B200SR3_API int b200sr3_num_snapshots(b200sr3_handle* h);
+
+/* The same call for HOST buffers (the end-to-end path bench.py times as `e2e`): cond is copied
+ * host->device, the chain runs with PHILOX noise, out is copied device->host, and the call
+ * returns after the copy has completed. cond/out should be pinned for full PCIe speed. */
+B200SR3_API int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int B, int R,
+                        float* out_host, void* stream);
+
+/* Introspection for layer-level parity tests: copy the activation a named layer produced in
+ * the most recent forward ("downs.0" ... "ups.18", "mid.0", "mid.1"; unet.py module names) to
+ * fp32 NCHW. *C/*H/*W are filled in; `dst` may be NULL to query the shape only. */
+B200SR3_API int b200sr3_layer_output(b200sr3_handle* h, const char* layer, float* dst, int* C, int* H, int* W,
+                         void* stream);
+
+/* Counters: kernels launched by the library inside the last step / sample call, and the number
+ * of conv (tcgen05) launches among them. */
+B200SR3_API int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int64_t* conv);
+
+/* Kernel-level entry used by the conv parity tests and by bench.py's roofline probe: one
+ * implicit-GEMM convolution on the tcgen05 path. x: fp32 NCHW [B,Cin,H,W]; w: fp32 OIHW
+ * [Cout,Cin,k,k] (k = 1 or 3, pad = k/2); stride 1 or 2; upsample2x applies a nearest 2x
+ * before the conv (unet.py:58-65); optional residual (fp32 NCHW, output shape) is added in
+ * the epilogue. Operands are rounded to bf16, accumulation is fp32, y is fp32 NCHW.
+ * If iters > 0 the conv kernel alone is launched `iters` more times and the average device
+ * time in milliseconds is written to *avg_ms (CUDA events on `stream`). */
+B200SR3_API int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias,
+                   const float* residual, int B, int Cin, int H, int W, int Cout, int k,
+                   int stride, int upsample2x, float* y, int iters, float* avg_ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR3_H_ */
