@@ -84,6 +84,11 @@ class GaussianDiffusion(nn.Module):
         self.noise_seed = 0       # base seed of the in-kernel Philox stream
         self._calls = 0
 
+    def __getstate__(self):       # engines hold device handles: never pickled / deep-copied
+        state = self.__dict__.copy()
+        state["_engines"] = {}
+        return state
+
     # ------------------------------------------------------------------ reference surface
     def set_loss(self, device):
         if self.loss_type == "l1":
@@ -265,6 +270,38 @@ class GaussianDiffusion(nn.Module):
     def super_resolution_batched(self, x_in, noise=None, seed=None):
         """[B,3,R,R] in -> [B,3,R,R] out (the reference returns only the last element)."""
         return self.sample_batched(x_in, noise=noise, seed=seed)
+
+    @torch.no_grad()
+    def sample_host(self, cond_host, out_host=None, seed=0):
+        """End-to-end call on HOST tensors (pinned for full PCIe speed): cond is copied to the
+        device, the full chain runs with Philox noise, the result is copied back; returns when
+        the copy has landed. This is the path bench.py reports as `e2e`."""
+        dev = self._sampling_device()
+        eng = self._engine(dev)
+        if cond_host.device.type != "cpu" or cond_host.dtype != torch.float32 or not cond_host.is_contiguous():
+            raise ValueError("b200sr3: sample_host expects a contiguous fp32 CPU tensor")
+        if out_host is None:
+            out_host = torch.empty_like(cond_host, pin_memory=True)
+        B, R = cond_host.shape[0], cond_host.shape[-1]
+        with torch.cuda.device(dev):
+            _lib.check(eng.lib.b200sr3_sample_host(eng.handle, _ptr(cond_host), C.c_uint64(int(seed)), B, R,
+                                                   _ptr(out_host), _stream()))
+        return out_host
+
+    def profile_step(self, B, R):
+        """Per-launch device times of one sampling step: list of (name, ms, flops, bytes)."""
+        eng = self._engine()
+        n_max = 1024
+        ms = (C.c_float * n_max)()
+        fl = (C.c_double * n_max)()
+        by = (C.c_double * n_max)()
+        names = C.create_string_buffer(64 * n_max)
+        n = C.c_int()
+        with torch.cuda.device(self._sampling_device()):
+            _lib.check(eng.lib.b200sr3_profile_step(eng.handle, B, R, n_max, ms, fl, by, names, len(names),
+                                                    C.byref(n), _stream()))
+        nm = names.value.decode().split("\n")
+        return [(nm[i], ms[i], fl[i], by[i]) for i in range(n.value)]
 
     def layer_output(self, name):
         """Activation of a UNet module ('downs.3', 'mid.0', ...) from the most recent forward."""

@@ -130,6 +130,14 @@ int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int64_t* conv) 
   });
 }
 
+int b200sr3_profile_step(b200sr3_handle* h, int B, int R, int max_ops, float* ms, double* flops, double* bytes,
+                         char* names, int names_len, int* n_ops, void* stream) {
+  return guarded([&] {
+    REQUIRE(ms && n_ops, "profile_step: null argument");
+    *n_ops = E(h).profile_step(B, R, max_ops, ms, flops, bytes, names, names_len, (cudaStream_t)stream);
+  });
+}
+
 int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias, const float* residual, int B,
                    int Cin, int H, int W, int Cout, int k, int stride, int upsample2x, float* y, int iters,
                    float* avg_ms, void* stream) {

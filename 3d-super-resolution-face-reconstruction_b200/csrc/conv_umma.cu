@@ -166,6 +166,11 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
   Op op;
   op.name = name;
   op.is_conv = true;
+  {
+    const double m = (double)out.B * out.H * out.W;
+    const double k = (double)main.taps * a.C + (res0 ? res0->C : 0) + (res1 ? res1->C : 0);
+    op.flops = 2.0 * m * (double)out.C * k;
+  }
   op.run = [pp, grid, bn](cudaStream_t s) {
     if (bn == 256) launch_conv<256, 4>(*pp, grid, s);
     else if (bn == 128) launch_conv<128, 3>(*pp, grid, s);

@@ -412,8 +412,9 @@ void Engine::build_workspace(Workspace& ws) {
     Act y = act(x0.H, x0.W, C);
     g->dst = y.ptr;
     g->swish = swish ? 1 : 0;
-    ws.ops.push_back(Op{name + ".gn_stats", false, [g](cudaStream_t s) { launch_gn_stats(*g, s); }});
-    ws.ops.push_back(Op{name + ".gn_apply", false, [g](cudaStream_t s) { launch_gn_apply(*g, s); }});
+    const double elems = (double)B * g->HW * C;
+    ws.ops.push_back(Op{name + ".gn_stats", false, [g](cudaStream_t s) { launch_gn_stats(*g, s); }, 0.0, 2.0 * elems});
+    ws.ops.push_back(Op{name + ".gn_apply", false, [g](cudaStream_t s) { launch_gn_apply(*g, s); }, 0.0, 4.0 * elems});
     return y;
   };
   auto conv = [&](const std::string& name, const Act& src, int taps, int stride, const PackedConv& w,
@@ -543,6 +544,44 @@ void Engine::ensure_graph(Workspace& ws) {
   cudaError_t e = cudaGraphInstantiate(&ws.graph, g, 0);
   cudaGraphDestroy(g);
   CUDA_CHECK(e);
+}
+
+int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, double* bytes, char* names,
+                         int names_len, cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  REQUIRE(T_sched_ > 0, "profile_step: no noise schedule installed");
+  Workspace& ws = workspace(B, R);
+  const int n = (int)ws.ops.size();
+  REQUIRE(n <= max_ops, "profile_step: output arrays too small");
+  const size_t numel = (size_t)B * cfg_.out_channel * R * R;
+  launch_philox_fill(ws.x, B, cfg_.out_channel, R, 1234, T_sched_, s);
+  write_ctl(T_sched_ - 1, B200SR3_NOISE_PHILOX, nullptr, 1234, (long long)numel, s);
+  ws.tail_plan->eps_out = nullptr;
+  ws.tail_plan->x = ws.x;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  for (int rep = 0; rep < 2; ++rep) {          // first repetition warms up
+    CUDA_CHECK(cudaEventRecord(ev[0], s));
+    for (int i = 0; i < n; ++i) {
+      ws.ops[i].run(s);
+      CUDA_CHECK(cudaEventRecord(ev[i + 1], s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  std::string all;
+  for (int i = 0; i < n; ++i) {
+    CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    if (flops) flops[i] = ws.ops[i].flops;
+    if (bytes) bytes[i] = ws.ops[i].bytes;
+    all += ws.ops[i].name;
+    all += '\n';
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (names && names_len > 0) {
+    strncpy(names, all.c_str(), (size_t)names_len - 1);
+    names[names_len - 1] = 0;
+  }
+  return n;
 }
 
 // ------------------------------------------------------------------------------- entry points

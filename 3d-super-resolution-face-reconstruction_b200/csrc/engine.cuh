@@ -47,6 +47,8 @@ struct Op {
   std::string name;
   bool is_conv = false;
   std::function<void(cudaStream_t)> run;
+  double flops = 0.0;   // algorithmic FLOPs (2*MAC on the reference graph) of one launch
+  double bytes = 0.0;   // algorithmic HBM bytes of one launch (HBM-bound kernels)
 };
 
 class Engine;
@@ -87,6 +89,9 @@ class Engine {
               float* out, float* snapshots, cudaStream_t s);
   void sample_host(const float* cond_host, uint64_t seed, int B, int R, float* out_host, cudaStream_t s);
   int num_snapshots() const;
+  // One eager step with a CUDA event between consecutive launches: per-op device time.
+  int profile_step(int B, int R, int max_ops, float* ms, double* flops, double* bytes, char* names,
+                   int names_len, cudaStream_t s);
   void layer_output(const std::string& layer, float* dst, int* C, int* H, int* W, cudaStream_t s);
 
   int64_t last_total = 0, last_conv = 0;

@@ -126,6 +126,13 @@ B200SR3_API int b200sr3_layer_output(b200sr3_handle* h, const char* layer, float
  * of conv (tcgen05) launches among them. */
 B200SR3_API int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int64_t* conv);
 
+/* Measurement aid for bench.py's roofline: runs ONE sampling step of a (B,R) batch eagerly with
+ * a CUDA event between consecutive launches and reports, per launch in chain order, the device
+ * time (ms), the algorithmic FLOPs (convs) and algorithmic HBM bytes (norm kernels), and the
+ * newline-separated op names. Not used on the sampling path. */
+B200SR3_API int b200sr3_profile_step(b200sr3_handle* h, int B, int R, int max_ops, float* ms, double* flops,
+                                     double* bytes, char* names, int names_len, int* n_ops, void* stream);
+
 /* Kernel-level entry used by the conv parity tests and by bench.py's roofline probe: one
  * implicit-GEMM convolution on the tcgen05 path. x: fp32 NCHW [B,Cin,H,W]; w: fp32 OIHW
  * [Cout,Cin,k,k] (k = 1 or 3, pad = k/2); stride 1 or 2; upsample2x applies a nearest 2x

@@ -1,0 +1,170 @@
+"""Parity of the CUDA sampling path (through the define_G / GaussianDiffusion drop-in, i.e.
+through the C ABI) with the reference: golden vectors produced by the real reference
+(tests/golden, oracle/make_golden.py) and the CPU oracle on fresh seeded inputs.
+
+Stated tolerances (north_star: "within a stated bf16/fp32 tolerance"):
+  TOL_EPS_REL   UNet output: rms error <= 1 % of the rms of eps, max error <= 6 % of it
+  TOL_STEP      teacher-forced x_{t-1}: max abs error <= 1e-3 (image range is 2); the
+                reference's own bf16-autocast error on this quantity is 5e-4 .. 7e-3
+  TOL_CHAIN     free-running T=10 chain, final image: max abs error <= 5e-3
+  PSNR_MIN      full T=400 free-running chain vs the reference's final image: >= 40 dB
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_net, synthetic_weights
+from oracle import sr3_oracle as O
+from oracle.weights import make_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL_EPS_RMS, TOL_EPS_MAX = 0.01, 0.06
+TOL_STEP = 1e-3
+TOL_CHAIN = 5e-3
+PSNR_MIN = 40.0
+
+
+@pytest.fixture(scope="module")
+def net10():
+    return build_net(10)
+
+
+@pytest.fixture(scope="module")
+def net400():
+    return build_net(400)
+
+
+def test_unet_forward_golden(golden_dir):
+    """R=64, harsher weights (gain 1.7), against the reference's own eps."""
+    g = np.load(os.path.join(golden_dir, "unet_r64.npz"))
+    net, _ = build_net(200, seed=int(g["weight_seed"]), gain=float(g["weight_gain"]))
+    x6 = torch.from_numpy(g["x6"]).cuda()
+    eps = net.unet_eps(x6[:, :3], x6[:, 3:], float(g["noise_level"][0, 0])).cpu()
+    ref = torch.from_numpy(g["eps"])
+    rms = float(ref.pow(2).mean().sqrt())
+    assert float((eps - ref).pow(2).mean().sqrt()) <= TOL_EPS_RMS * rms
+    assert float((eps - ref).abs().max()) <= TOL_EPS_MAX * rms
+
+
+@pytest.mark.parametrize("R,B", [(16, 3), (32, 2), (128, 1)])
+def test_unet_forward_vs_oracle_layers(R, B):
+    """Every module output of one forward, NHWC bf16 on the device vs fp32 NCHW in the oracle."""
+    import ctypes as C
+    net, mopt = build_net(10)
+    sd = synthetic_weights(0, 1.0)
+    cond, noise = make_inputs(B, R, 1, seed=R)
+    taps = {}
+    with torch.no_grad():
+        ref = O.unet_forward(sd, mopt, torch.cat([cond, noise[0]], 1), torch.full((B, 1), 0.8), taps)
+    eps = net.unet_eps(cond.cuda(), noise[0].cuda(), 0.8).cpu()
+    rms = float(ref.pow(2).mean().sqrt())
+    assert float((eps - ref).pow(2).mean().sqrt()) <= TOL_EPS_RMS * rms
+    assert float((eps - ref).abs().max()) <= TOL_EPS_MAX * rms
+    eng = net._engine()
+    for name, t in taps.items():
+        if name == "final_conv":
+            continue
+        buf = torch.empty(t.shape, device="cuda")
+        c, h, w = C.c_int(), C.c_int(), C.c_int()
+        rc = eng.lib.b200sr3_layer_output(eng.handle, name.encode(), C.c_void_p(buf.data_ptr()), C.byref(c),
+                                          C.byref(h), C.byref(w), C.c_void_p(0))
+        assert rc == 0 and (c.value, h.value, w.value) == tuple(t.shape[1:]), name
+        lrms = float(t.pow(2).mean().sqrt())
+        assert float((buf.cpu() - t).pow(2).mean().sqrt()) <= 0.015 * lrms, name
+
+
+def test_teacher_forced_steps_golden(golden_dir, net400):
+    """Every stored step of the reference's T=400 chain: same x_t, cond and z_t in, x_{t-1} out."""
+    g = np.load(os.path.join(golden_dir, "steps_r32_T400.npz"))
+    net, _ = net400
+    cond = torch.from_numpy(g["cond"]).cuda()
+    worst = 0.0
+    for i, t in enumerate(g["t"].tolist()):
+        out = net.p_sample(torch.from_numpy(g["x_t"][i]).cuda(), t, condition_x=cond,
+                           noise=torch.from_numpy(g["z_t"][i]).cuda()).cpu()
+        worst = max(worst, float((out - torch.from_numpy(g["x_tm1"][i])).abs().max()))
+    assert worst <= TOL_STEP, worst
+
+
+def test_free_running_chain_golden(golden_dir, net10):
+    """T=10 chain with the reference's noise list injected; also the reference's return quirks."""
+    g = np.load(os.path.join(golden_dir, "chain_r32_T10.npz"))
+    net, _ = net10
+    cond, noise = torch.from_numpy(g["cond"]).cuda(), torch.from_numpy(g["noise"]).cuda()
+    out = net.super_resolution_batched(cond, noise=noise).cpu()
+    ref = torch.from_numpy(g["xs"][-1])
+    assert float((out - ref).abs().max()) <= TOL_CHAIN
+    for b in range(out.shape[0]):
+        assert O.psnr_uint8(out[b], ref[b]) >= 50.0
+    snaps = net.super_resolution(cond, continous=True, noise=noise).cpu()      # diffusion.py:210-213
+    assert snaps.shape == g["snapshots"].shape
+    assert float((snaps - torch.from_numpy(g["snapshots"])).abs().max()) <= TOL_CHAIN
+    last = net.super_resolution(cond, continous=False, noise=noise).cpu()      # ret_img[-1] -> [3,R,R]
+    assert last.shape == (3, 32, 32) and torch.equal(last, out[-1])
+
+
+def test_full_T400_chain_psnr(golden_dir, net400):
+    """Config 1 (8->32) at its full T: final image vs the reference's, max-abs and PSNR."""
+    g = np.load(os.path.join(golden_dir, "steps_r32_T400.npz"))
+    net, _ = net400
+    cond, noise = make_inputs(2, 32, 400, seed=321)
+    assert np.array_equal(cond.numpy(), g["cond"])
+    out = net.super_resolution_batched(cond.cuda(), noise=noise.cuda()).cpu()
+    ref = torch.from_numpy(g["final"])
+    psnr = min(O.psnr_uint8(out[b], ref[b]) for b in range(2))
+    assert psnr >= PSNR_MIN, psnr
+    assert float((out - ref).abs().max()) <= 0.05
+
+
+def test_graph_loop_equals_stepwise(net10):
+    """The CUDA-graph chain and T separate step() calls run the same kernels: bit-identical."""
+    net, _ = net10
+    cond, noise = make_inputs(3, 16, 10, seed=5)
+    cond, noise = cond.cuda(), noise.cuda()
+    out = net.super_resolution_batched(cond, noise=noise)
+    x = noise[0]
+    for t in reversed(range(10)):
+        x = net.p_sample(x, t, condition_x=cond, noise=noise[10 - t] if t > 0 else None)
+    assert torch.equal(out, x)
+    assert torch.equal(out, net.super_resolution_batched(cond, noise=noise))   # replay determinism
+
+
+def test_batch_invariance_at_full_size():
+    """Size-independent property at the headline shape (R=128, T=600 schedule): a face's step
+    does not depend on which other faces share its batch, so sharding cannot change results."""
+    net, _ = build_net(600)
+    cond, noise = make_inputs(5, 128, 2, seed=77)
+    cond, x, z = cond.cuda(), noise[0].cuda(), noise[1].cuda()
+    full = net.p_sample(x, 599, condition_x=cond, noise=z)
+    for sl in (slice(0, 1), slice(1, 3), slice(3, 5)):
+        part = net.p_sample(x[sl].contiguous(), 599, condition_x=cond[sl].contiguous(), noise=z[sl].contiguous())
+        assert torch.equal(part, full[sl])
+    assert torch.isfinite(full).all()
+    t0 = net.p_sample(x, 0, condition_x=cond, noise=z)                         # t == 0 ignores the noise
+    assert torch.equal(t0, net.p_sample(x, 0, condition_x=cond, noise=None))
+    assert float(t0.abs().max()) <= 1.0 + 1e-6                                 # C1[0]=1, C2[0]=0: x = clamp(x0)
+
+
+def test_philox_noise_stream(net10):
+    net, _ = net10
+    cond, _ = make_inputs(2, 32, 1, seed=1)
+    cond = cond.cuda()
+    a = net.super_resolution_batched(cond, seed=11)
+    b = net.super_resolution_batched(cond, seed=11)
+    c = net.super_resolution_batched(cond, seed=12)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.isfinite(a).all()
+
+
+def test_errors_surface_as_exceptions(net10):
+    from b200sr3._lib import B200Error
+    net, _ = net10
+    with pytest.raises(B200Error):
+        net.p_sample(torch.zeros(1, 3, 24, 24).cuda(), 0, condition_x=torch.zeros(1, 3, 24, 24).cuda())   # R not 2^k
+    with pytest.raises(B200Error):
+        net.p_sample(torch.zeros(1, 3, 16, 16).cuda(), 10, condition_x=torch.zeros(1, 3, 16, 16).cuda())  # t >= T
+    with pytest.raises(ValueError):
+        net.super_resolution_batched(torch.zeros(1, 3, 16, 16).cuda(), noise=torch.zeros(3, 1, 3, 16, 16).cuda())

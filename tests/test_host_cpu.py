@@ -1,0 +1,100 @@
+"""Host-side mirror of define_G / GaussianDiffusion: key set, schedule buffers, error behaviour."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200sr3
+from conftest import synthetic_weights
+
+
+def _net(T=10, phase="val"):
+    opt = {"phase": phase, "sr": {"model": b200sr3.configs.model_opt(T)}}
+    return b200sr3.define_G(opt), opt
+
+
+def test_state_dict_contract():
+    net, opt = _net()
+    sd = synthetic_weights(0, 1.0)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    assert opt["sr"]["model"]["unet"]["norm_groups"] == 32          # networks.py:89-90 side effect
+    assert sum(p.numel() for p in net.parameters()) == 92556931
+    net.set_new_noise_schedule(opt["sr"]["model"]["beta_schedule"]["val"], [torch.device("cpu")])
+    assert len(net.state_dict()) == 337 + 12
+
+
+def test_named_configs_cover_the_reference_yamls():
+    for (lr, hr), T in b200sr3.configs.TIMESTEPS.items():
+        for m in ("model2", "model3"):
+            opt = b200sr3.configs.named(f"sr_sr3_VGGF2_{lr}_{hr}_{m}")
+            assert opt["sr"]["model"]["beta_schedule"]["val"]["n_timestep"] == T
+            assert opt["r_resolution"] == hr
+
+
+def test_schedule_buffers_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "schedules.npz"))
+    net, _ = _net()
+    for T in (100, 600, 1000):
+        sched = b200sr3.configs.model_opt(T)["beta_schedule"]["val"]
+        net.set_new_noise_schedule(sched, [torch.device("cpu")])
+        assert net.num_timesteps == T
+        assert np.array_equal(net.sqrt_recip_alphas_cumprod.numpy(), g[f"T{T}_sqrt_recip_ac"])
+        assert np.array_equal(net.posterior_mean_coef1.numpy(), g[f"T{T}_coef1"])
+        assert np.array_equal(net.posterior_log_variance_clipped.numpy(), g[f"T{T}_post_logvar"])
+        assert np.array_equal(net.sqrt_alphas_cumprod_prev, g[f"T{T}_sqrt_ac_prev"])
+    with pytest.raises(NotImplementedError):
+        net.set_new_noise_schedule(dict(sched, schedule="nope"), [torch.device("cpu")])
+
+
+def test_torch_training_path_matches_oracle_unet():
+    """The differentiable torch forward kept for the training loss is the same function."""
+    from oracle import sr3_oracle as O
+    net, opt = _net()
+    sd = synthetic_weights(0, 1.0)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = torch.randn(1, 6, 16, 16, generator=torch.Generator().manual_seed(1))
+    nl = torch.full((1, 1), 0.4)
+    with torch.no_grad():
+        a = net.denoise_fn(x, nl)
+        b = O.unet_forward(sd, opt["sr"]["model"], x, nl)
+    assert float((a - b).abs().max()) < 1e-5
+
+
+def test_orthogonal_init_in_train_phase():
+    net, _ = _net(phase="train")
+    w = net.denoise_fn.state_dict()["downs.1.res_block.block1.block.3.weight"].flatten(1)
+    assert torch.allclose(w @ w.t(), torch.eye(w.shape[0]), atol=1e-4)
+    assert float(net.denoise_fn.state_dict()["downs.1.res_block.block1.block.3.bias"].abs().max()) == 0.0
+
+
+def test_sampling_has_no_cpu_fallback():
+    net, opt = _net()
+    net.set_new_noise_schedule(opt["sr"]["model"]["beta_schedule"]["val"], [torch.device("cpu")])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.super_resolution(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(NotImplementedError):
+        b200sr3.define_G({"phase": "val", "sr": {"model": dict(opt["sr"]["model"], which_model_G="ddpm")}})
+
+
+def test_l1_loss_forward_runs_on_cpu():
+    net, opt = _net()
+    net.set_new_noise_schedule(opt["sr"]["model"]["beta_schedule"]["train"], [torch.device("cpu")])
+    net.set_loss(torch.device("cpu"))
+    g = torch.Generator().manual_seed(0)
+    batch = {"HR": torch.rand(1, 3, 16, 16, generator=g) * 2 - 1, "SR": torch.rand(1, 3, 16, 16, generator=g) * 2 - 1}
+    loss = net(batch)
+    assert loss.dim() == 0 and torch.isfinite(loss)
+
+
+def test_product_synthetic_generator_matches_oracle_copy():
+    from b200sr3 import synthetic
+    from oracle.weights import make_inputs, state_dict_digest
+    net, _ = _net()
+    assert state_dict_digest(synthetic.state_dict(net, 0, 1.0)) == state_dict_digest(synthetic_weights(0, 1.0))
+    c1, n1 = synthetic.inputs(2, 16, 3, seed=5)
+    c2, n2 = make_inputs(2, 16, 3, seed=5)
+    assert torch.equal(c1, c2) and torch.equal(n1, n2)
