@@ -6,17 +6,24 @@
 namespace b200sr3 {
 
 // =============================================================================== GroupNorm
+// Both passes run 384-thread CTAs: 384 is divisible by every channel-vector count C/8 the UNet
+// produces (8,16,24,32,48,64,96,128), so a thread keeps ONE 8-channel column for its whole life —
+// no index division in the loop, scale/shift live in registers, and each thread keeps four
+// independent 16-byte loads in flight.
+//
 // Pass 1: per-CTA partial (sum, sumsq) per channel; the last CTA of an image (ticket) reduces
 // the partials in a fixed order (deterministic), forms the group statistics and writes the
 // per-(image, channel) scale/shift that pass 2 (or a fused consumer) applies.
-__global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
-  __shared__ float red[256 * 16];
-  __shared__ float chan[2048 * 2];
+constexpr int GN_THREADS = 384;
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
+  __shared__ float red[GN_THREADS * 16];
+  __shared__ float chan[1024 * 2];
   __shared__ float gstat[64 * 2];
   __shared__ int is_last;
   const int C = g.C0 + g.C1;
   const int Cv = C >> 3;
-  const int rows = 256 / Cv;
+  const int rows = GN_THREADS / Cv;
   const int tid = threadIdx.x;
   const int cv = tid % Cv, r = tid / Cv;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -27,32 +34,42 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (r < rows) {
+  {
     const int c = cv * 8;
     const bf16* base;
     int cs;
     if (c < g.C0) { base = g.src0 + c; cs = g.C0; } else { base = g.src1 + (c - g.C0); cs = g.C1; }
     base += (size_t)b * g.HW * cs;
-    for (int p = p_begin + r; p < p_end; p += rows) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs));
-      float f[8];
-      unpack8(v, f);
+    int p = p_begin + r;
+    for (; p + 3 * rows < p_end; p += 4 * rows) {
+      uint4 v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * rows) * cs));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; p < p_end; p += rows) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[tid * 16 + i] = s[i]; red[tid * 16 + 8 + i] = q[i]; }
   __syncthreads();
-  if (r == 0) {
-    float* dst = g.partial + ((size_t)(b * g.chunks + chunk) * C + cv * 8) * 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = 0.f, d = 0.f;
-      for (int rr = 0; rr < rows; ++rr) { a += red[(rr * Cv + cv) * 16 + i]; d += red[(rr * Cv + cv) * 16 + 8 + i]; }
-      dst[2 * i] = a;
-      dst[2 * i + 1] = d;
-    }
+  // reduce over rows: thread (j < Cv*16) owns one (channel-vector, slot) pair
+  for (int j = tid; j < Cv * 16; j += GN_THREADS) {
+    const int v = j >> 4, slot = j & 15;
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += red[(rr * Cv + v) * 16 + slot];
+    // partial layout: [b][chunk][c][2] with slot<8 -> sum of channel v*8+slot, else sumsq
+    g.partial[((size_t)(b * g.chunks + chunk) * C + v * 8 + (slot & 7)) * 2 + (slot >> 3)] = a;
   }
   __threadfence();
   __syncthreads();
@@ -60,7 +77,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += GN_THREADS) {
     float a = 0.f, d = 0.f;
     for (int k = 0; k < g.chunks; ++k) {
       const float2 v = *reinterpret_cast<const float2*>(g.partial + ((size_t)(b * g.chunks + k) * C + c) * 2);
@@ -82,7 +99,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
     gstat[2 * tid + 1] = rsqrtf(var + 1e-5f);
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += GN_THREADS) {
     const int grp = c / cg;
     const float sc = gstat[2 * grp + 1] * g.gamma[c];
     float2 o;
@@ -93,57 +110,84 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnPlan g) {
   if (tid == 0) g.ticket[b] = 0;
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnPlan g) {
+// Pass 2: grid (apply_chunks, B); a CTA streams a contiguous pixel range of one image.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int apply_chunks) {
   const int C = g.C0 + g.C1;
   const int Cv = C >> 3;
-  const long long total = (long long)g.B * g.HW * Cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % Cv);
-    const long long bp = idx / Cv;           // b*HW + p
-    const int b = (int)(bp / g.HW);
-    const int c = cv * 8;
-    const bf16* src = (c < g.C0) ? g.src0 + bp * g.C0 + c : g.src1 + bp * g.C1 + (c - g.C0);
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-    float f[8];
-    unpack8(v, f);
+  const int rows = GN_THREADS / Cv;
+  const int cv = threadIdx.x % Cv, r = threadIdx.x / Cv;
+  const int b = blockIdx.y;
+  const int ppc = (g.HW + apply_chunks - 1) / apply_chunks;
+  const int p_begin = blockIdx.x * ppc;
+  const int p_end = min(g.HW, p_begin + ppc);
+  const int c = cv * 8;
+  float sc[8], sh[8];
+  {
     const float4* ss = reinterpret_cast<const float4*>(g.scale_shift + ((size_t)b * C + c) * 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(ss + i);        // (scale, shift) x 2 channels
-      float y0 = fmaf(f[2 * i], t.x, t.y);
-      float y1 = fmaf(f[2 * i + 1], t.z, t.w);
-      if (g.swish) { y0 = swish_f(y0); y1 = swish_f(y1); }
-      f[2 * i] = y0;
-      f[2 * i + 1] = y1;
+      const float4 t = __ldg(ss + i);
+      sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
     }
-    *reinterpret_cast<uint4*>(g.dst + bp * C + c) = pack8(f);
   }
+  const bf16* base;
+  int cs;
+  if (c < g.C0) { base = g.src0 + c; cs = g.C0; } else { base = g.src1 + (c - g.C0); cs = g.C1; }
+  base += (size_t)b * g.HW * cs;
+  bf16* dst = g.dst + (size_t)b * g.HW * C + c;
+  const bool do_swish = g.swish != 0;
+  auto emit = [&](const uint4& v, int p) {
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], sc[i], sh[i]);
+      f[i] = do_swish ? swish_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)p * C) = pack8(f);
+  };
+  int p = p_begin + r;
+  for (; p + 3 * rows < p_end; p += 4 * rows) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * rows) * cs));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(v[u], p + u * rows);
+  }
+  for (; p < p_end; p += rows) emit(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), p);
 }
 
 void gn_choose_chunks(GnPlan& g) {
   const int C = g.C0 + g.C1;
   long long per_img = (long long)g.HW * C;
-  long long ch = per_img / (256LL * 8 * 8);
+  long long ch = per_img / ((long long)GN_THREADS * 8 * 16);   // ~16 vectors per thread
   if (ch < 1) ch = 1;
   if (ch > 64) ch = 64;
   if (ch > g.HW) ch = g.HW;
   g.chunks = (int)ch;
 }
 
-void launch_gn_stats(const GnPlan& g, cudaStream_t s) {
+static void gn_check(const GnPlan& g) {
   const int C = g.C0 + g.C1;
-  REQUIRE(C % 8 == 0 && g.C0 % 8 == 0 && C <= 2048 && C % g.groups == 0 && g.groups <= 64,
+  REQUIRE(C % 8 == 0 && g.C0 % 8 == 0 && C <= 1024 && C % g.groups == 0 && g.groups <= 64,
           "GroupNorm: unsupported channel count");
-  gn_stats_kernel<<<dim3(g.chunks, g.B), 256, 0, s>>>(g);
+  REQUIRE(GN_THREADS % (C / 8) == 0, "GroupNorm: C/8 must divide 384");
+}
+
+void launch_gn_stats(const GnPlan& g, cudaStream_t s) {
+  gn_check(g);
+  gn_stats_kernel<<<dim3(g.chunks, g.B), GN_THREADS, 0, s>>>(g);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_gn_apply(const GnPlan& g, cudaStream_t s) {
-  const long long total = (long long)g.B * g.HW * ((g.C0 + g.C1) >> 3);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  gn_apply_kernel<<<(int)blocks, 256, 0, s>>>(g);
+  gn_check(g);
+  const int C = g.C0 + g.C1;
+  long long ch = (long long)g.HW * C / ((long long)GN_THREADS * 8 * 8);     // ~8 vectors per thread
+  if (ch < 1) ch = 1;
+  if (ch > g.HW) ch = g.HW;
+  if (ch > 1024) ch = 1024;
+  gn_apply_kernel<<<dim3((int)ch, g.B), GN_THREADS, 0, s>>>(g, (int)ch);
   CUDA_CHECK(cudaGetLastError());
 }
 

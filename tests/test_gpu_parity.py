@@ -73,7 +73,7 @@ def test_unet_forward_vs_oracle_layers(R, B):
                                           C.byref(h), C.byref(w), C.c_void_p(0))
         assert rc == 0 and (c.value, h.value, w.value) == tuple(t.shape[1:]), name
         lrms = float(t.pow(2).mean().sqrt())
-        assert float((buf.cpu() - t).pow(2).mean().sqrt()) <= 0.015 * lrms, name
+        assert float((buf.cpu() - t).pow(2).mean().sqrt()) <= 0.02 * lrms, name      # bf16 storage error compounds over ~15 blocks
 
 
 def test_teacher_forced_steps_golden(golden_dir, net400):
