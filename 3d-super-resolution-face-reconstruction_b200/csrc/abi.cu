@@ -171,13 +171,10 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
     in.ptr = (bf16*)dalloc(in.elems() * sizeof(bf16));
     launch_nchw_to_nhwc(x, in.ptr, B, Cin, H, W, s);
     Act src = in;
-    if (upsample2x) {
-      src.H = 2 * H; src.W = 2 * W;
-      src.ptr = (bf16*)dalloc(src.elems() * sizeof(bf16));
-      launch_upsample2x(in.ptr, src.ptr, B, H, W, Cin, s);
-    }
     Act out;
-    out.B = B; out.H = src.H / stride; out.W = src.W / stride; out.C = Cout;
+    out.B = B; out.C = Cout;
+    out.H = (upsample2x ? 2 * H : H) / stride;
+    out.W = (upsample2x ? 2 * W : W) / stride;
     out.ptr = (bf16*)dalloc(out.elems() * sizeof(bf16));
     bf16* res = nullptr;
     if (residual) {
@@ -187,14 +184,23 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
     PackedConv pc;
     const int taps = k * k;
     const int cpad = (Cin + CONV_BLOCK_K - 1) / CONV_BLOCK_K * CONV_BLOCK_K;
-    pc.cout = Cout; pc.taps = taps; pc.cin_main = Cin; pc.k_total = taps * cpad;
-    pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
-    launch_pack_conv_weight(w, pc.w, Cout, Cin, taps, cpad, 0, pc.k_total, s);
+    pc.cout = Cout; pc.taps = taps; pc.cin_main = Cin;
+    if (upsample2x) {
+      REQUIRE(k == 3 && stride == 1, "conv2d: upsample2x needs a 3x3 stride-1 conv");
+      pc.up_folded = true;
+      pc.k_total = 4 * cpad;
+      pc.w = (bf16*)dalloc((size_t)4 * Cout * pc.k_total * sizeof(bf16));
+      launch_pack_upfold_weight(w, pc.w, Cout, Cin, cpad, s);
+    } else {
+      pc.k_total = taps * cpad;
+      pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
+      launch_pack_conv_weight(w, pc.w, Cout, Cin, taps, cpad, 0, pc.k_total, s);
+    }
     ConvSource cs;
-    cs.act = src; cs.taps = taps; cs.stride = stride;
+    cs.act = src; cs.taps = taps; cs.stride = stride; cs.upsample2x = upsample2x != 0;
     int force_bn = 0;
     if (const char* g = getenv("B200SR3_BLOCK_N")) force_bn = atoi(g);
-    Op op = make_conv_op("conv2d", cs, nullptr, nullptr, pc, bias, 0, nullptr, res, out, force_bn);
+    Op op = make_conv_op("conv2d", cs, nullptr, nullptr, pc, bias, 0, nullptr, res, out, force_bn, nullptr);
     op.run(s);
     launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
     CUDA_CHECK(cudaStreamSynchronize(s));

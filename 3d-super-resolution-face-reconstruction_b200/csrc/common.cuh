@@ -52,6 +52,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 struct Act {  // NHWC bf16 activation
   bf16* ptr = nullptr;
+  float* stats = nullptr;   // chansum [B][C][2]: per-(image, channel) sum and sum of squares (GroupNorm input)
   int B = 0, H = 0, W = 0, C = 0;
   size_t elems() const { return (size_t)B * H * W * C; }
 };

@@ -56,51 +56,89 @@ static void encode_weight_map(CUtensorMap* m, const bf16* w, int k_total, int co
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <int BN, int ST>
-static void launch_conv(const ConvParams& p, dim3 grid, cudaStream_t s) {
+static void launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
   conv_umma_kernel<BN, ST><<<grid, CONV_THREADS, ConvSmem<BN, ST>::TOTAL, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
 
+// smem ring depth per BLOCK_N: 192 KB of stages in every case
+constexpr int ST64 = 8, ST128 = 6, ST256 = 4;
+static int g_num_sms = 148;
+
 void conv_init_device() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvSmem<64, 4>::TOTAL));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvSmem<128, 3>::TOTAL));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvSmem<256, 4>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64, ST64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<64, ST64>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128, ST128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<128, ST128>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256, ST256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<256, ST256>::TOTAL));
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+}
+
+bool conv_can_fuse_stats(const Act& out, bool upsample2x) {
+  // a warp's 32 accumulator rows must belong to one image, and a tile to at most two
+  const int hw = upsample2x ? (out.H / 2) * (out.W / 2) : out.H * out.W;
+  return hw >= 64;
 }
 
 Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0, const Act* res1,
                 const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl,
-                const bf16* residual, const Act& out, int force_block_n) {
+                const bf16* residual, const Act& out, int force_block_n, const ConvStats* stats) {
   const Act& a = main.act;
+  const bool up = main.upsample2x;
   REQUIRE(main.stride == 1 || main.stride == 2, "conv: stride must be 1 or 2");
   REQUIRE(main.taps == 9 || main.taps == 1, "conv: kernel must be 1x1 or 3x3");
   REQUIRE(a.C % 8 == 0 && out.C % 8 == 0, "conv: channel counts must be multiples of 8");
   REQUIRE(a.C == w.cin_main && out.C == w.cout && main.taps == w.taps, "conv: weight/activation mismatch");
-  REQUIRE(out.H * main.stride == a.H && out.W * main.stride == a.W && out.B == a.B, "conv: output shape mismatch");
+  if (up) {
+    REQUIRE(main.stride == 1 && main.taps == 9 && !res0 && !res1 && w.up_folded,
+            "conv: folded upsample supports a plain 3x3 stride-1 conv only");
+    REQUIRE(out.H == 2 * a.H && out.W == 2 * a.W && out.B == a.B, "conv: output shape mismatch");
+  } else {
+    REQUIRE(out.H * main.stride == a.H && out.W * main.stride == a.W && out.B == a.B, "conv: output shape mismatch");
+    REQUIRE(!w.up_folded, "conv: weights were packed for a folded upsample");
+  }
   REQUIRE(is_pow2(out.W) && is_pow2(out.H), "conv: spatial dims must be powers of two");
 
   auto pp = std::make_shared<ConvParams>();
   ConvParams& p = *pp;
   memset(&p, 0, sizeof(p));
-  // ---- tile box over the output pixels
-  p.bw = std::min(out.W, CONV_BLOCK_M);
-  p.bh = std::min(out.H, CONV_BLOCK_M / p.bw);
+  // ---- tile box over the pixel space the tiles walk (the source grid when the upsample is folded)
+  const int PH = up ? a.H : out.H, PW = up ? a.W : out.W;
+  p.bw = std::min(PW, CONV_BLOCK_M);
+  p.bh = std::min(PH, CONV_BLOCK_M / p.bw);
   p.bb = CONV_BLOCK_M / (p.bw * p.bh);
-  p.tiles_w = out.W / p.bw;
-  p.tiles_h = out.H / p.bh;
+  p.tiles_w = PW / p.bw;
+  p.tiles_h = PH / p.bh;
   p.tiles_b = ceil_div(out.B, p.bb);
-  p.B = out.B; p.Hout = out.H; p.Wout = out.W; p.Cout = out.C;
-  p.out_sy = p.out_sx = 1; p.out_oy = p.out_ox = 0;
+  p.B = out.B; p.Hout = PH; p.Wout = PW; p.Cout = out.C;
   p.out_H = out.H; p.out_W = out.W;
+  p.num_par = up ? 4 : 1;
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
   p.residual = residual; p.out = out.ptr;
 
   // ---- A maps + tap list (order must match the packed weight's K order)
   int nt = 0, kblocks = 0;
   const int cb_main = ceil_div(a.C, CONV_BLOCK_K);
-  if (main.stride == 1) {
+  if (up) {
+    encode_act_map(&p.a_map[0], a.ptr, a.C, a.W, a.H, a.B, (size_t)a.C, (size_t)a.W * a.C,
+                   (size_t)a.H * a.W * a.C, p.bw, p.bh, p.bb);
+    // output (2i+py, 2j+px) reads source rows {i-1, i} (py = 0) or {i, i+1} (py = 1); same for columns
+    for (int par = 0; par < 4; ++par) {
+      const int py = par >> 1, px = par & 1;
+      for (int t = 0; t < 4; ++t) {
+        ConvTap& tp = p.taps[nt++];
+        tp.map = 0;
+        tp.dh = (int16_t)((t >> 1) - 1 + py);
+        tp.dw = (int16_t)((t & 1) - 1 + px);
+        tp.cblocks = (int16_t)cb_main;
+      }
+    }
+    p.num_taps = 4;
+    kblocks = 4 * cb_main;
+  } else if (main.stride == 1) {
     encode_act_map(&p.a_map[0], a.ptr, a.C, a.W, a.H, a.B, (size_t)a.C, (size_t)a.W * a.C,
                    (size_t)a.H * a.W * a.C, p.bw, p.bh, p.bb);
     for (int t = 0; t < main.taps; ++t) {
@@ -128,40 +166,60 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
       kblocks += cb_main;
     }
   }
-  const Act* rs[2] = {res0, res1};
-  const int rc[2] = {w.c_res0, w.c_res1};
-  for (int i = 0; i < 2; ++i) {
-    if (!rs[i]) { REQUIRE(rc[i] == 0, "conv: missing res_conv source"); continue; }
-    REQUIRE(rs[i]->C == rc[i] && rs[i]->H == out.H && rs[i]->W == out.W && rs[i]->B == out.B,
-            "conv: res_conv source mismatch");
-    const Act& r = *rs[i];
-    encode_act_map(&p.a_map[1 + i], r.ptr, r.C, r.W, r.H, r.B, (size_t)r.C, (size_t)r.W * r.C,
-                   (size_t)r.H * r.W * r.C, p.bw, p.bh, p.bb);
-    ConvTap& tp = p.taps[nt++];
-    tp.map = (int16_t)(1 + i); tp.dh = 0; tp.dw = 0;
-    tp.cblocks = (int16_t)ceil_div(r.C, CONV_BLOCK_K);
-    kblocks += tp.cblocks;
+  if (!up) {
+    const Act* rs[2] = {res0, res1};
+    const int rc[2] = {w.c_res0, w.c_res1};
+    for (int i = 0; i < 2; ++i) {
+      if (!rs[i]) { REQUIRE(rc[i] == 0, "conv: missing res_conv source"); continue; }
+      REQUIRE(rs[i]->C == rc[i] && rs[i]->H == out.H && rs[i]->W == out.W && rs[i]->B == out.B,
+              "conv: res_conv source mismatch");
+      const Act& r = *rs[i];
+      encode_act_map(&p.a_map[1 + i], r.ptr, r.C, r.W, r.H, r.B, (size_t)r.C, (size_t)r.W * r.C,
+                     (size_t)r.H * r.W * r.C, p.bw, p.bh, p.bb);
+      ConvTap& tp = p.taps[nt++];
+      tp.map = (int16_t)(1 + i); tp.dh = 0; tp.dw = 0;
+      tp.cblocks = (int16_t)ceil_div(r.C, CONV_BLOCK_K);
+      kblocks += tp.cblocks;
+    }
+    p.num_taps = nt;
   }
   REQUIRE(nt <= CONV_MAX_TAPS, "conv: too many taps");
   REQUIRE(kblocks * CONV_BLOCK_K == w.k_total, "conv: packed weight K does not match the tap list");
-  p.num_taps = nt;
   p.num_kblocks = kblocks;
 
-  // ---- N tile: largest of 256/128/64 that divides Cout and still yields >= 148 CTAs
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  // ---- N tile: the candidate with the lowest modelled time. Per K block a tile costs
+  // max(MMA cycles = 2*bn, operand bytes / L2-to-SM rate) and a CTA runs ceil(tiles / SMs) tiles.
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.num_par;
   int bn = 64;
   if (force_block_n) {
     bn = force_block_n;
   } else {
+    double best = 1e30;
     const int cand[3] = {256, 128, 64};
     for (int c : cand) {
       if (out.C % c != 0) continue;
-      if (m_tiles * (out.C / c) >= 148 || c == 64) { bn = c; break; }
+      const double per_kb = std::max(2.0 * c, (16384.0 + 128.0 * c) / 64.0);
+      const double rounds = (double)ceil_div(m_tiles * (out.C / c), g_num_sms);
+      const double cost = rounds * (kblocks * per_kb + 400.0 + 6.0 * c);
+      if (cost < best) { best = cost; bn = c; }
     }
   }
   REQUIRE(bn == 64 || bn == 128 || bn == 256, "conv: BLOCK_N must be 64, 128 or 256");
-  encode_weight_map(&p.w_map, w.w, w.k_total, w.cout, bn);
-  const dim3 grid(m_tiles, ceil_div(out.C, bn));
+  REQUIRE(out.C % bn == 0, "conv: BLOCK_N must divide Cout");
+  p.tiles_n = out.C / bn;
+  p.total_tiles = m_tiles * p.tiles_n;
+  encode_weight_map(&p.w_map, w.w, w.k_total, w.cout * p.num_par, bn);
+
+  if (stats) {
+    REQUIRE(conv_can_fuse_stats(out, up), "conv: statistics cannot be fused for this shape");
+    REQUIRE(p.bb <= 2, "conv: internal tile shape error");
+    p.stat_chansum = stats->chansum;
+    p.stat_partial = stats->partial;
+    p.stat_ticket = stats->ticket;
+    p.stat_slots = p.num_par * (p.bb == 1 ? p.tiles_h * p.tiles_w : 1);
+    REQUIRE(p.stat_slots <= stats->max_slots, "conv: statistics scratch too small");
+  }
+  const int grid = std::min(p.total_tiles, g_num_sms);
 
   Op op;
   op.name = name;
@@ -169,14 +227,22 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
   {
     const double m = (double)out.B * out.H * out.W;
     const double k = (double)main.taps * a.C + (res0 ? res0->C : 0) + (res1 ? res1->C : 0);
-    op.flops = 2.0 * m * (double)out.C * k;
+    op.flops = 2.0 * m * (double)out.C * k;     // reference graph (full-resolution 3x3 for Upsample)
   }
   op.run = [pp, grid, bn](cudaStream_t s) {
-    if (bn == 256) launch_conv<256, 4>(*pp, grid, s);
-    else if (bn == 128) launch_conv<128, 3>(*pp, grid, s);
-    else launch_conv<64, 4>(*pp, grid, s);
+    if (bn == 256) launch_conv<256, ST256>(*pp, grid, s);
+    else if (bn == 128) launch_conv<128, ST128>(*pp, grid, s);
+    else launch_conv<64, ST64>(*pp, grid, s);
   };
   return op;
+}
+
+int conv_stat_slots(const Act& out, bool upsample2x) {
+  const int PH = upsample2x ? out.H / 2 : out.H, PW = upsample2x ? out.W / 2 : out.W;
+  const int bw = std::min(PW, CONV_BLOCK_M);
+  const int bh = std::min(PH, CONV_BLOCK_M / bw);
+  const int bb = CONV_BLOCK_M / (bw * bh);
+  return (upsample2x ? 4 : 1) * (bb == 1 ? (PH / bh) * (PW / bw) : 1);
 }
 
 }  // namespace b200sr3

@@ -4,20 +4,26 @@
 // 120-121) except the 6->64 head and the 64->3 tail, which are CUDA-core kernels.
 //
 // GEMM view:  D[M, N] = A[M, K] * W[N, K]^T
-//   M = output pixels. One CTA owns 128 of them, chosen as a (bb x bh x bw) box of the NHWC
+//   M = output pixels. One tile owns 128 of them, chosen as a (bb x bh x bw) box of the NHWC
 //       activation so that ONE 4-D TMA box load, shifted by the filter tap, fetches the
-//       A tile of that tap: rows = pixels, 64 channels (128 B) per row, 128B-swizzled — i.e.
+//       A tile of that tap: rows = pixels, 64 channels (128 B) per row, 128B-swizzled - i.e.
 //       exactly the K-major SWIZZLE_128B operand layout tcgen05 wants. Out-of-bounds rows/cols
 //       (the conv's zero padding, or batch rows past B) are zero-filled by the TMA unit.
-//   N = output channels, BLOCK_N per CTA (64/128/256) = TMEM columns of the fp32 accumulator.
+//   N = output channels, BLOCK_N per tile (64/128/256) = TMEM columns of the fp32 accumulator.
 //   K = sum over "taps" of 64-channel blocks: the 9 (or 1) filter taps of the main source,
 //       then optional 1x1 segments of other sources (the ResnetBlock's res_conv folded into
 //       block2's GEMM, unet.py:103-110). Weights are pre-packed [Cout][K] in the same order.
 // Stride-2 convs use four "parity" tensor maps over the same buffer (base offset + doubled
-// strides) so a tap is again one plain box load.
+// strides) so a tap is again one plain box load. Upsample(nearest 2x)+conv3x3 (unet.py:58-65)
+// is folded: each output parity (y&1, x&1) is a 2x2 conv over the LOW-resolution source with
+// pre-summed weights, so the 4x tensor is never materialised (num_par = 4 tile groups).
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> +bias (+residual) -> bf16).
+// The kernel is PERSISTENT: grid = min(tiles, SMs); a CTA walks tiles blockIdx.x, +gridDim.x, ...
+// Warp roles (256 threads): warp 0 = TMA producer (runs ahead across tiles through a STAGES-deep
+// smem ring), warp 1 = MMA issuer (one lane; alternates between two TMEM accumulators),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> +bias[t] (+residual) -> bf16
+// stores, and per-channel sum / sum-of-squares of the fp32 outputs for the NEXT GroupNorm), which
+// overlaps the MMAs of the following tile.
 #pragma once
 #include "common.cuh"
 
@@ -25,7 +31,7 @@ namespace b200sr3 {
 
 constexpr int CONV_BLOCK_M = 128;
 constexpr int CONV_BLOCK_K = 64;   // bf16 elements = one 128-byte swizzle row
-constexpr int CONV_MAX_TAPS = 12;
+constexpr int CONV_MAX_TAPS = 16;
 constexpr int CONV_THREADS = 256;
 
 struct ConvTap {
@@ -37,19 +43,26 @@ struct ConvTap {
 struct alignas(64) ConvParams {
   CUtensorMap a_map[4];
   CUtensorMap w_map;
-  ConvTap taps[CONV_MAX_TAPS];
-  int num_taps;
-  int num_kblocks;
-  int tiles_w, tiles_h, tiles_b;   // tile grid over the OUTPUT pixels
+  ConvTap taps[CONV_MAX_TAPS];     // num_par groups of num_taps entries
+  int num_taps;                    // taps per group
+  int num_kblocks;                 // K blocks per tile
+  int num_par;                     // 1, or 4 when a nearest-2x upsample is folded in
+  int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
   int bw, bh, bb;                  // box (tile) extent in pixels, bw*bh*bb == 128
-  int B, Hout, Wout, Cout;         // output tensor [B, Hout, Wout, Cout] bf16 NHWC
-  int out_sy, out_sx, out_oy, out_ox;  // output pixel = (h*out_sy + out_oy, w*out_sx + out_ox)
-  int out_H, out_W;                // dims of the tensor `out` points at (differs when scattering)
+  int B, Hout, Wout, Cout;         // pixel space the tiles walk ([B,Hout,Wout]; source res if num_par==4)
+  int out_H, out_W;                // dims of the tensor `out` points at ((2*Hout, 2*Wout) if num_par==4)
   const float* bias;               // [Cout] (may be null)
   int bias_t_stride;               // if non-zero, row ctl->t of a [rows][stride] table is used
   const StepCtl* ctl;
   const bf16* residual;            // same shape as out, added in the epilogue (may be null)
   bf16* out;
+  // GroupNorm statistics of the output (null: not wanted). chansum[b][c] = (sum, sumsq) over the
+  // image's pixels; tiles write partial[b][slot][c][2] and the last tile of an (image, n-tile)
+  // (ticket) adds the slots in a fixed order, so the result is deterministic.
+  float* stat_chansum;
+  float* stat_partial;
+  int* stat_ticket;                // [B * tiles_n], zero on entry, self-resetting
+  int stat_slots;                  // partial slots per image (num_par * tiles per image)
 };
 
 #ifdef __CUDACC__
@@ -67,6 +80,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -184,9 +200,28 @@ struct ConvSmem {
   static constexpr int A_BYTES = CONV_BLOCK_M * CONV_BLOCK_K * 2;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * CONV_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAT_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAT_BYTES = 2 * 4 * 2 * BLOCK_N * 4;         // [buf][warp][sum|sq][col] fp32
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;            // + barriers + align slack
 };
+
+// lane l ends up with the sum over the warp's 32 lanes of v[l] (31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float keep = upper ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -194,23 +229,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using S = ConvSmem<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  float* sstat = reinterpret_cast<float*>(smem_gen + S::STAT_OFFSET);
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full; then the TMEM address.
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the
+  // TMEM address and two "last tile of the image" flags.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  int* s_last = reinterpret_cast<int*>(smem_gen + S::BAR_OFFSET + 8 * (2 * STAGES + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  int m_tile = blockIdx.x;
-  const int tw = m_tile % p.tiles_w;
-  m_tile /= p.tiles_w;
-  const int th = m_tile % p.tiles_h;
-  const int tb = m_tile / p.tiles_h;
-  const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.bb;
-  const int n0 = blockIdx.y * BLOCK_N;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.w_map);
@@ -221,32 +253,54 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tmem_full_bar(b), 1);
+      ptx::mbar_init(tmem_empty_bar(b), 128);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, BLOCK_N);
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, 2 * BLOCK_N);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // tile -> (n tile, box origin, parity group); n varies fastest so concurrently running CTAs
+  // share the A tile in L2.
+  struct Tile { int n_tile, w0, h0, b0, par; };
+  auto decode = [&](int tile) {
+    Tile t;
+    t.n_tile = tile % p.tiles_n; tile /= p.tiles_n;
+    t.w0 = (tile % p.tiles_w) * p.bw; tile /= p.tiles_w;
+    t.h0 = (tile % p.tiles_h) * p.bh; tile /= p.tiles_h;
+    t.b0 = (tile % p.tiles_b) * p.bb;
+    t.par = tile / p.tiles_b;
+    return t;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      int stage = 0, kb = 0;
+      int stage = 0;
       uint32_t phase = 0;
-      for (int ti = 0; ti < p.num_taps; ++ti) {
-        const ConvTap tap = p.taps[ti];
-        const CUtensorMap* amap = &p.a_map[tap.map];
-        for (int cb = 0; cb < tap.cblocks; ++cb, ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
-          const uint32_t sb = sa + S::A_BYTES;
-          ptx::mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-          ptx::tma_load_4d(sa, amap, full_bar(stage), cb * CONV_BLOCK_K, w0 + tap.dw, h0 + tap.dh, b0);
-          ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const Tile t = decode(tile);
+        const ConvTap* taps = p.taps + t.par * p.num_taps;
+        const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N;
+        int kb = 0;
+        for (int ti = 0; ti < p.num_taps; ++ti) {
+          const ConvTap tap = taps[ti];
+          const CUtensorMap* amap = &p.a_map[tap.map];
+          for (int cb = 0; cb < tap.cblocks; ++cb, ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+            const uint32_t sb = sa + S::A_BYTES;
+            ptx::mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+            ptx::tma_load_4d(sa, amap, full_bar(stage), cb * CONV_BLOCK_K, t.w0 + tap.dw, t.h0 + tap.dh, t.b0);
+            ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K, wrow);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -256,67 +310,151 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
-        ptx::mbar_wait(full_bar(stage), phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        ptx::mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
-        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < CONV_BLOCK_K / 16; ++k) {
-          // advancing 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in the address field
-          const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
-          const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
-          ptx::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < CONV_BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in the address field
+            const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
+            const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        ptx::umma_commit(tmem_full_bar(buf));   // accumulator complete
       }
-      ptx::umma_commit(tmem_full_bar);        // accumulator complete
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int wq = warp & 3;                  // TMEM lane quarter this warp may read
     const int row = wq * 32 + lane;           // GEMM row = pixel inside the box
+    const int tid_e = threadIdx.x - 128;
     const int lw = row % p.bw;
     const int lh = (row / p.bw) % p.bh;
     const int lb = row / (p.bw * p.bh);
-    const int b = b0 + lb, h = h0 + lh, w = w0 + lw;
-    const bool valid = (b < p.B) && (h < p.Hout) && (w < p.Wout);
-    const size_t pix = ((size_t)b * p.out_H + (size_t)(h * p.out_sy + p.out_oy)) * p.out_W +
-                       (size_t)(w * p.out_sx + p.out_ox);
-    bf16* out_row = p.out + pix * p.Cout + n0;
-    const bf16* res_row = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+    const bool do_stats = p.stat_chansum != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
+    const int osc = p.num_par == 4 ? 2 : 1;
+    const int tiles_per_img = (p.bb == 1) ? p.tiles_h * p.tiles_w : 1;
 
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const Tile t = decode(tile);
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int n0 = t.n_tile * BLOCK_N;
+      const int b = t.b0 + lb, h = t.h0 + lh, w = t.w0 + lw;
+      const bool valid = (b < p.B) && (h < p.Hout) && (w < p.Wout);
+      const size_t pix = ((size_t)b * p.out_H + (size_t)(h * osc + (t.par >> 1))) * p.out_W +
+                         (size_t)(w * osc + (t.par & 1));
+      bf16* out_row = p.out + pix * p.Cout + n0;
+      const bf16* res_row = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+      float* sb = sstat + buf * (4 * 2 * BLOCK_N);
+
+      ptx::mbar_wait(tmem_full_bar(buf), use & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * BLOCK_N);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
-      ptx::tmem_ld_wait();
-      if (valid) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int n = n0 + c0 + j;
-          if (n < p.Cout) {
-            float f[8];
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-            if (bias) {
-              const float4 b0v = __ldg(reinterpret_cast<const float4*>(bias + n));
-              const float4 b1v = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-              f[0] += b0v.x; f[1] += b0v.y; f[2] += b0v.z; f[3] += b0v.w;
-              f[4] += b1v.x; f[5] += b1v.y; f[6] += b1v.z; f[7] += b1v.w;
-            }
-            if (res_row) {
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        }
+        if (valid) {
+          if (res_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
               float r[8];
               unpack8(*reinterpret_cast<const uint4*>(res_row + c0 + j), r);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += r[e];
+              for (int e = 0; e < 8; ++e) f[j + e] += r[e];
             }
-            *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
+        }
+        if (do_stats) {
+          float q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = valid ? f[j] : 0.f;
+            q[j] = f[j] * f[j];
+          }
+          const float s_sum = warp_transpose_sum(f, lane);
+          const float s_sq = warp_transpose_sum(q, lane);
+          sb[(wq * 2 + 0) * BLOCK_N + c0 + lane] = s_sum;
+          sb[(wq * 2 + 1) * BLOCK_N + c0 + lane] = s_sq;
+        }
+      }
+      // all of this thread's TMEM reads have completed: hand the accumulator back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty_bar(buf));
+
+      if (do_stats) {
+        epi_bar_sync();
+        const int nimg = p.bb >= 2 ? 2 : 1;       // host guarantees bb <= 2 when stats are fused
+        const int wpi = 4 / nimg;
+        const int slot = t.par * tiles_per_img + ((p.bb == 1) ? (t.h0 / p.bh) * p.tiles_w + t.w0 / p.bw : 0);
+        for (int item = tid_e; item < nimg * 2 * BLOCK_N; item += 128) {
+          const int col = item % BLOCK_N;
+          const int st = (item / BLOCK_N) & 1;
+          const int ib = item / (2 * BLOCK_N);
+          float a = 0.f;
+          for (int ww = 0; ww < wpi; ++ww) a += sb[((ib * wpi + ww) * 2 + st) * BLOCK_N + col];
+          const int bi = t.b0 + ib;
+          if (bi < p.B) {
+            const size_t ch = (size_t)(n0 + col);
+            if (p.stat_slots == 1) p.stat_chansum[((size_t)bi * p.Cout + ch) * 2 + st] = a;
+            else p.stat_partial[(((size_t)bi * p.stat_slots + slot) * p.Cout + ch) * 2 + st] = a;
+          }
+        }
+        if (p.stat_slots > 1) {
+          __threadfence();
+          epi_bar_sync();
+          if (tid_e < 2) {
+            int last = 0;
+            const int bi = t.b0 + tid_e;
+            if (tid_e < nimg && bi < p.B) {
+              int* tk = p.stat_ticket + bi * p.tiles_n + t.n_tile;
+              last = (atomicAdd(tk, 1) == p.stat_slots - 1);
+              if (last) *tk = 0;
+            }
+            s_last[tid_e] = last;
+          }
+          epi_bar_sync();
+          for (int ib = 0; ib < nimg; ++ib) {
+            if (!s_last[ib]) continue;
+            __threadfence();
+            const int bi = t.b0 + ib;
+            for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
+              // item = col*2 + st: consecutive threads read consecutive floats of a slot row
+              const size_t off = (size_t)n0 * 2 + item;
+              const float* src = p.stat_partial + (size_t)bi * p.stat_slots * p.Cout * 2 + off;
+              float a = 0.f;
+              for (int sl = 0; sl < p.stat_slots; ++sl) a += __ldcg(src + (size_t)sl * p.Cout * 2);
+              p.stat_chansum[(size_t)bi * p.Cout * 2 + off] = a;
+            }
           }
         }
       }
@@ -325,7 +463,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 #endif  // __CUDACC__
 

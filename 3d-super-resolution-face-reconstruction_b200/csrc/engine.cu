@@ -257,10 +257,21 @@ void Engine::finalize_weights(cudaStream_t s) {
         launch_pack_head_weight(T_(l.name + ".weight"), head_w_, l.cout, l.c_x, s);
         break;
       }
-      case LayerKind::Down:
-      case LayerKind::Up: {
+      case LayerKind::Down: {
         PackedConv* pc = pack(l.name + ".conv", l.name + ".conv", l.cout, l.c_x, 9, "", 0, 0);
         pc->bias = T_(l.name + ".conv.bias");
+        break;
+      }
+      case LayerKind::Up: {
+        // Upsample(nearest 2x) + conv3x3 -> four parity 2x2 convs over the low-res tensor
+        PackedConv pc;
+        pc.cout = l.cout; pc.taps = 9; pc.cin_main = l.c_x; pc.up_folded = true;
+        const int cpad = round_up(l.c_x, CONV_BLOCK_K);
+        pc.k_total = 4 * cpad;
+        pc.w = (bf16*)dalloc((size_t)4 * l.cout * pc.k_total * sizeof(bf16));
+        launch_pack_upfold_weight(T_(l.name + ".conv.weight"), pc.w, l.cout, l.c_x, cpad, s);
+        pc.bias = T_(l.name + ".conv.bias");
+        convs_[l.name + ".conv"] = pc;
         break;
       }
       case LayerKind::Final: {
@@ -384,6 +395,7 @@ void Engine::build_workspace(Workspace& ws) {
     Act a;
     a.B = B; a.H = H; a.W = W; a.C = C;
     a.ptr = (bf16*)dalloc(a.elems() * sizeof(bf16));
+    a.stats = (float*)dalloc((size_t)B * C * 2 * sizeof(float));
     return a;
   };
   const int oc = cfg_.out_channel;
@@ -394,37 +406,59 @@ void Engine::build_workspace(Workspace& ws) {
   CUDA_CHECK(cudaMemset(ws.cond, 0, img));
   const int G = cfg_.norm_groups;
 
-  // GroupNorm (+Swish) of [x0 | x1] into a fresh tensor; two launches.
+  // statistics of a tensor no conv epilogue produced (head conv output, spatial sizes < 8x8)
+  auto chan_stats = [&](const std::string& name, const Act& x) {
+    auto g = std::make_shared<ChanStatsPlan>();
+    g->src = x.ptr; g->B = B; g->HW = x.H * x.W; g->C = x.C;
+    g->chunks = chan_stats_chunks(g->HW, g->C);
+    g->chansum = x.stats;
+    if (g->chunks > 1) {
+      g->partial = (float*)dalloc((size_t)B * g->chunks * x.C * 2 * sizeof(float));
+      g->ticket = (int*)dalloc((size_t)B * sizeof(int));
+      CUDA_CHECK(cudaMemset(g->ticket, 0, (size_t)B * sizeof(int)));
+    }
+    ws.ops.push_back(Op{name + ".chan_stats", false, [g](cudaStream_t s) { launch_chan_stats(*g, s); }, 0.0,
+                        2.0 * (double)B * g->HW * g->C});
+  };
+  // GroupNorm (+Swish) of [x0 | x1] into a fresh tensor (one HBM pass; statistics come with the inputs)
   auto group_norm = [&](const std::string& name, const Act& x0, const Act* x1, const std::string& gkey, bool swish) {
     auto g = std::make_shared<GnPlan>();
-    g->src0 = x0.ptr; g->C0 = x0.C;
-    g->src1 = x1 ? x1->ptr : nullptr; g->C1 = x1 ? x1->C : 0;
+    g->src0 = x0.ptr; g->C0 = x0.C; g->stats0 = x0.stats;
+    g->src1 = x1 ? x1->ptr : nullptr; g->C1 = x1 ? x1->C : 0; g->stats1 = x1 ? x1->stats : nullptr;
     g->B = B; g->HW = x0.H * x0.W; g->groups = G;
     const int C = g->C0 + g->C1;
     REQUIRE(C % G == 0, "GroupNorm: channels not divisible by norm_groups");
     g->gamma = T_(gkey + ".weight");
     g->beta = T_(gkey + ".bias");
-    gn_choose_chunks(*g);
-    g->partial = (float*)dalloc((size_t)B * g->chunks * C * 2 * sizeof(float));
-    g->scale_shift = (float*)dalloc((size_t)B * C * 2 * sizeof(float));
-    g->ticket = (int*)dalloc((size_t)B * sizeof(int));
-    CUDA_CHECK(cudaMemset(g->ticket, 0, (size_t)B * sizeof(int)));
     Act y = act(x0.H, x0.W, C);
     g->dst = y.ptr;
     g->swish = swish ? 1 : 0;
     const double elems = (double)B * g->HW * C;
-    ws.ops.push_back(Op{name + ".gn_stats", false, [g](cudaStream_t s) { launch_gn_stats(*g, s); }, 0.0, 2.0 * elems});
     ws.ops.push_back(Op{name + ".gn_apply", false, [g](cudaStream_t s) { launch_gn_apply(*g, s); }, 0.0, 4.0 * elems});
     return y;
   };
-  auto conv = [&](const std::string& name, const Act& src, int taps, int stride, const PackedConv& w,
+  auto conv = [&](const std::string& name, const Act& src, int taps, int stride, bool up, const PackedConv& w,
                   const Act* r0, const Act* r1, const float* bias, int bias_stride, const bf16* residual,
-                  int Ho, int Wo) {
+                  int Ho, int Wo, bool want_stats) {
     Act y = act(Ho, Wo, w.cout);
     ConvSource cs;
-    cs.act = src; cs.taps = taps; cs.stride = stride;
-    ws.ops.push_back(make_conv_op(name, cs, r0, r1, w, bias, bias_stride, ctl_, residual, y, force_block_n_));
+    cs.act = src; cs.taps = taps; cs.stride = stride; cs.upsample2x = up;
+    ConvStats st;
+    const bool fuse = want_stats && conv_can_fuse_stats(y, up);
+    if (fuse) {
+      st.chansum = y.stats;
+      st.max_slots = conv_stat_slots(y, up);
+      if (st.max_slots > 1) {
+        st.partial = (float*)dalloc((size_t)B * st.max_slots * w.cout * 2 * sizeof(float));
+        const size_t nt = (size_t)B * (w.cout / 64);
+        st.ticket = (int*)dalloc(nt * sizeof(int));
+        CUDA_CHECK(cudaMemset(st.ticket, 0, nt * sizeof(int)));
+      }
+    }
+    ws.ops.push_back(make_conv_op(name, cs, r0, r1, w, bias, bias_stride, ctl_, residual, y, force_block_n_,
+                                  fuse ? &st : nullptr));
     ws.n_conv++;
+    if (want_stats && !fuse) chan_stats(name, y);
     return y;
   };
 
@@ -442,23 +476,19 @@ void Engine::build_workspace(Workspace& ws) {
         ws.ops.push_back(Op{l.name, false, [=](cudaStream_t s) {
           launch_head_conv(cond, xw, cc, oc, hw, hb, B, R, co, dst, s);
         }});
+        chan_stats(l.name, cur);
         feats.push_back(cur);
         break;
       }
       case LayerKind::Down: {
         const PackedConv& pc = convs_.at(l.name + ".conv");
-        cur = conv(l.name, cur, 9, 2, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H / 2, cur.W / 2);
+        cur = conv(l.name, cur, 9, 2, false, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H / 2, cur.W / 2, true);
         feats.push_back(cur);
         break;
       }
       case LayerKind::Up: {
         const PackedConv& pc = convs_.at(l.name + ".conv");
-        Act up = act(cur.H * 2, cur.W * 2, cur.C);
-        const Act src = cur;
-        ws.ops.push_back(Op{l.name + ".upsample", false, [src, up](cudaStream_t s) {
-          launch_upsample2x(src.ptr, up.ptr, src.B, src.H, src.W, src.C, s);
-        }});
-        cur = conv(l.name, up, 9, 1, pc, nullptr, nullptr, pc.bias, 0, nullptr, up.H, up.W);
+        cur = conv(l.name, cur, 9, 1, true, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H * 2, cur.W * 2, true);
         break;
       }
       case LayerKind::Res: {
@@ -475,24 +505,25 @@ void Engine::build_workspace(Workspace& ws) {
         const Act xin = cur;
         Act xn = group_norm(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0", true);
         const PackedConv& c1 = convs_.at(l.name + ".c1");
-        Act h = conv(l.name + ".conv1", xn, 9, 1, c1, nullptr, nullptr, table_ + noise_off_.at(l.name),
-                     noise_total_, nullptr, xin.H, xin.W);
+        Act h = conv(l.name + ".conv1", xn, 9, 1, false, c1, nullptr, nullptr, table_ + noise_off_.at(l.name),
+                     noise_total_, nullptr, xin.H, xin.W, true);
         Act hn = group_norm(l.name + ".block2", h, nullptr, rb + ".block2.block.0", true);
         const PackedConv& c2 = convs_.at(l.name + ".c2");
         const bool has_res = c2.c_res0 > 0;
-        cur = conv(l.name + ".conv2", hn, 9, 1, c2, has_res ? &xin : nullptr, (has_res && is_up) ? &skip : nullptr,
-                   c2.bias, 0, has_res ? nullptr : xin.ptr, xin.H, xin.W);
+        cur = conv(l.name + ".conv2", hn, 9, 1, false, c2, has_res ? &xin : nullptr,
+                   (has_res && is_up) ? &skip : nullptr, c2.bias, 0, has_res ? nullptr : xin.ptr, xin.H, xin.W, true);
         if (l.attn) {
           const Act ain = cur;
           Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);
-          Act qkv = conv(l.name + ".attn.qkv", an, 1, 1, convs_.at(l.name + ".qkv"), nullptr, nullptr, nullptr, 0,
-                         nullptr, ain.H, ain.W);
+          Act qkv = conv(l.name + ".attn.qkv", an, 1, 1, false, convs_.at(l.name + ".qkv"), nullptr, nullptr, nullptr,
+                         0, nullptr, ain.H, ain.W, false);
           Act ao = act(ain.H, ain.W, ain.C);
           ws.ops.push_back(Op{l.name + ".attn.core", false, [qkv, ao](cudaStream_t s) {
             launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
           }});
           const PackedConv& po = convs_.at(l.name + ".out");
-          cur = conv(l.name + ".attn.out", ao, 1, 1, po, nullptr, nullptr, po.bias, 0, ain.ptr, ain.H, ain.W);
+          cur = conv(l.name + ".attn.out", ao, 1, 1, false, po, nullptr, nullptr, po.bias, 0, ain.ptr, ain.H, ain.W,
+                     true);
         }
         if (l.name.compare(0, 6, "downs.") == 0) feats.push_back(cur);
         break;

@@ -39,6 +39,7 @@ struct PackedConv {     // weights of one tensor-core conv
   int taps = 9;         // main segment: 9 or 1
   int cin_main = 0;     // channels of the main source
   int c_res0 = 0, c_res1 = 0;   // folded 1x1 res_conv segments (0 = none)
+  bool up_folded = false;       // [4*Cout][4*Cin]: parity 2x2 convs of Upsample(nearest 2x)+conv3x3
   float* bias = nullptr;        // static bias [Cout] (null when the bias comes from the table)
 };
 
@@ -139,10 +140,19 @@ struct ConvSource {
   Act act;            // source activation
   int taps = 9;       // 9: 3x3 pad 1; 1: 1x1
   int stride = 1;     // 1 or 2 (main source only)
+  bool upsample2x = false;   // the conv reads nearest-2x(act) (unet.py:58-65), folded into 4 parity convs
 };
+struct ConvStats {    // where the epilogue leaves the GroupNorm statistics of the output
+  float* chansum = nullptr;   // [B][Cout][2]
+  float* partial = nullptr;   // [B][max_slots][Cout][2]
+  int* ticket = nullptr;      // [B * Cout/64] zeroed
+  int max_slots = 0;
+};
+bool conv_can_fuse_stats(const Act& out, bool upsample2x);
+int conv_stat_slots(const Act& out, bool upsample2x);
 Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0, const Act* res1,
                 const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl,
-                const bf16* residual, const Act& out, int force_block_n);
+                const bf16* residual, const Act& out, int force_block_n, const ConvStats* stats);
 // Shared-memory opt-in for every conv kernel instance (once per process / device).
 void conv_init_device();
 

@@ -6,22 +6,24 @@
 namespace b200sr3 {
 
 // =============================================================================== GroupNorm
-// Both passes run 384-thread CTAs: 384 is divisible by every channel-vector count C/8 the UNet
+// Statistics arrive as per-(image, channel) (sum, sumsq) pairs "chansum[b][c][2]", produced in the
+// epilogue of the conv that wrote the tensor (conv_umma.cuh) or, for tensors no tensor-core conv
+// can cover (the head conv, spatial sizes below 8x8), by chan_stats_kernel below. Groups may
+// straddle the seam of a channel concat (unet.py:261), which is why the sums are kept per channel
+// and grouped only here.
+//
+// Both kernels run 384-thread CTAs: 384 is divisible by every channel-vector count C/8 the UNet
 // produces (8,16,24,32,48,64,96,128), so a thread keeps ONE 8-channel column for its whole life —
 // no index division in the loop, scale/shift live in registers, and each thread keeps four
 // independent 16-byte loads in flight.
-//
-// Pass 1: per-CTA partial (sum, sumsq) per channel; the last CTA of an image (ticket) reduces
-// the partials in a fixed order (deterministic), forms the group statistics and writes the
-// per-(image, channel) scale/shift that pass 2 (or a fused consumer) applies.
 constexpr int GN_THREADS = 384;
 
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
+// Per-CTA partial (sum, sumsq) per channel; the last CTA of an image (ticket) reduces the
+// partials in a fixed order (deterministic) into chansum.
+__global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g) {
   __shared__ float red[GN_THREADS * 16];
-  __shared__ float chan[1024 * 2];
-  __shared__ float gstat[64 * 2];
   __shared__ int is_last;
-  const int C = g.C0 + g.C1;
+  const int C = g.C;
   const int Cv = C >> 3;
   const int rows = GN_THREADS / Cv;
   const int tid = threadIdx.x;
@@ -35,16 +37,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   {
-    const int c = cv * 8;
-    const bf16* base;
-    int cs;
-    if (c < g.C0) { base = g.src0 + c; cs = g.C0; } else { base = g.src1 + (c - g.C0); cs = g.C1; }
-    base += (size_t)b * g.HW * cs;
+    const bf16* base = g.src + (size_t)b * g.HW * C + cv * 8;
     int p = p_begin + r;
     for (; p + 3 * rows < p_end; p += 4 * rows) {
       uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * rows) * cs));
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * rows) * C));
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -55,7 +53,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
     }
     for (; p < p_end; p += rows) {
       float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C)), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
@@ -64,28 +62,45 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
   for (int i = 0; i < 8; ++i) { red[tid * 16 + i] = s[i]; red[tid * 16 + 8 + i] = q[i]; }
   __syncthreads();
   // reduce over rows: thread (j < Cv*16) owns one (channel-vector, slot) pair
+  float* out = (g.chunks == 1) ? g.chansum + (size_t)b * C * 2 : g.partial + (size_t)(b * g.chunks + chunk) * C * 2;
   for (int j = tid; j < Cv * 16; j += GN_THREADS) {
     const int v = j >> 4, slot = j & 15;
     float a = 0.f;
     for (int rr = 0; rr < rows; ++rr) a += red[(rr * Cv + v) * 16 + slot];
-    // partial layout: [b][chunk][c][2] with slot<8 -> sum of channel v*8+slot, else sumsq
-    g.partial[((size_t)(b * g.chunks + chunk) * C + v * 8 + (slot & 7)) * 2 + (slot >> 3)] = a;
+    // layout [c][2] with slot<8 -> sum of channel v*8+slot, else sumsq
+    out[(size_t)(v * 8 + (slot & 7)) * 2 + (slot >> 3)] = a;
   }
+  if (g.chunks == 1) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) is_last = (atomicAdd(&g.ticket[b], 1) == g.chunks - 1);
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  for (int j = tid; j < C * 2; j += GN_THREADS) {
+    float a = 0.f;
+    for (int k = 0; k < g.chunks; ++k) a += __ldcg(g.partial + (size_t)(b * g.chunks + k) * C * 2 + j);
+    g.chansum[(size_t)b * C * 2 + j] = a;
+  }
+  if (tid == 0) g.ticket[b] = 0;
+}
+
+// y = [swish]((x - mean_g) * rstd_g * gamma + beta) over [src0 | src1]; grid (apply_chunks, B):
+// a CTA forms the group statistics of its image from chansum, then streams a pixel range.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int apply_chunks) {
+  __shared__ float chan[1024 * 2];
+  __shared__ float gstat[64 * 2];
+  const int C = g.C0 + g.C1;
+  const int Cv = C >> 3;
+  const int rows = GN_THREADS / Cv;
+  const int tid = threadIdx.x;
+  const int cv = tid % Cv, r = tid / Cv;
+  const int b = blockIdx.y;
   for (int c = tid; c < C; c += GN_THREADS) {
-    float a = 0.f, d = 0.f;
-    for (int k = 0; k < g.chunks; ++k) {
-      const float2 v = *reinterpret_cast<const float2*>(g.partial + ((size_t)(b * g.chunks + k) * C + c) * 2);
-      a += v.x;
-      d += v.y;
-    }
-    chan[2 * c] = a;
-    chan[2 * c + 1] = d;
+    const float2 v = (c < g.C0) ? *reinterpret_cast<const float2*>(g.stats0 + ((size_t)b * g.C0 + c) * 2)
+                                : *reinterpret_cast<const float2*>(g.stats1 + ((size_t)b * g.C1 + (c - g.C0)) * 2);
+    chan[2 * c] = v.x;
+    chan[2 * c + 1] = v.y;
   }
   __syncthreads();
   const int cg = C / g.groups;
@@ -99,36 +114,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnPlan g) {
     gstat[2 * tid + 1] = rsqrtf(var + 1e-5f);
   }
   __syncthreads();
-  for (int c = tid; c < C; c += GN_THREADS) {
-    const int grp = c / cg;
-    const float sc = gstat[2 * grp + 1] * g.gamma[c];
-    float2 o;
-    o.x = sc;
-    o.y = g.beta[c] - gstat[2 * grp] * sc;
-    *reinterpret_cast<float2*>(g.scale_shift + ((size_t)b * C + c) * 2) = o;
-  }
-  if (tid == 0) g.ticket[b] = 0;
-}
-
-// Pass 2: grid (apply_chunks, B); a CTA streams a contiguous pixel range of one image.
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int apply_chunks) {
-  const int C = g.C0 + g.C1;
-  const int Cv = C >> 3;
-  const int rows = GN_THREADS / Cv;
-  const int cv = threadIdx.x % Cv, r = threadIdx.x / Cv;
-  const int b = blockIdx.y;
   const int ppc = (g.HW + apply_chunks - 1) / apply_chunks;
   const int p_begin = blockIdx.x * ppc;
   const int p_end = min(g.HW, p_begin + ppc);
   const int c = cv * 8;
   float sc[8], sh[8];
-  {
-    const float4* ss = reinterpret_cast<const float4*>(g.scale_shift + ((size_t)b * C + c) * 2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(ss + i);
-      sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int grp = (c + i) / cg;
+    sc[i] = gstat[2 * grp + 1] * __ldg(g.gamma + c + i);
+    sh[i] = __ldg(g.beta + c + i) - gstat[2 * grp] * sc[i];
   }
   const bf16* base;
   int cs;
@@ -157,33 +152,28 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int appl
   for (; p < p_end; p += rows) emit(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), p);
 }
 
-void gn_choose_chunks(GnPlan& g) {
-  const int C = g.C0 + g.C1;
-  long long per_img = (long long)g.HW * C;
+int chan_stats_chunks(int HW, int C) {
+  long long per_img = (long long)HW * C;
   long long ch = per_img / ((long long)GN_THREADS * 8 * 16);   // ~16 vectors per thread
   if (ch < 1) ch = 1;
   if (ch > 64) ch = 64;
-  if (ch > g.HW) ch = g.HW;
-  g.chunks = (int)ch;
+  if (ch > HW) ch = HW;
+  return (int)ch;
 }
 
-static void gn_check(const GnPlan& g) {
-  const int C = g.C0 + g.C1;
-  REQUIRE(C % 8 == 0 && g.C0 % 8 == 0 && C <= 1024 && C % g.groups == 0 && g.groups <= 64,
-          "GroupNorm: unsupported channel count");
-  REQUIRE(GN_THREADS % (C / 8) == 0, "GroupNorm: C/8 must divide 384");
-}
-
-void launch_gn_stats(const GnPlan& g, cudaStream_t s) {
-  gn_check(g);
-  gn_stats_kernel<<<dim3(g.chunks, g.B), GN_THREADS, 0, s>>>(g);
+void launch_chan_stats(const ChanStatsPlan& g, cudaStream_t s) {
+  REQUIRE(g.C % 8 == 0 && g.C <= 1024 && GN_THREADS % (g.C / 8) == 0, "chan_stats: unsupported channel count");
+  chan_stats_kernel<<<dim3(g.chunks, g.B), GN_THREADS, 0, s>>>(g);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_gn_apply(const GnPlan& g, cudaStream_t s) {
-  gn_check(g);
   const int C = g.C0 + g.C1;
-  long long ch = (long long)g.HW * C / ((long long)GN_THREADS * 8 * 8);     // ~8 vectors per thread
+  REQUIRE(C % 8 == 0 && g.C0 % 8 == 0 && C <= 1024 && C % g.groups == 0 && g.groups <= 64,
+          "GroupNorm: unsupported channel count");
+  REQUIRE(GN_THREADS % (C / 8) == 0, "GroupNorm: C/8 must divide 384");
+  REQUIRE(g.stats0 && (g.C1 == 0 || g.stats1), "GroupNorm: missing channel statistics");
+  long long ch = (long long)g.HW * C / ((long long)GN_THREADS * 8 * 16);     // ~16 vectors per thread
   if (ch < 1) ch = 1;
   if (ch > g.HW) ch = g.HW;
   if (ch > 1024) ch = 1024;
@@ -501,30 +491,6 @@ void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStre
   CUDA_CHECK(cudaGetLastError());
 }
 
-// =============================================================================== upsample
-__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst,
-                                                         int B, int H, int W, int Cv) {
-  const long long total = (long long)B * 4 * H * W * Cv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % Cv);
-    long long p = idx / Cv;
-    const int xo = (int)(p % (2 * W)); p /= 2 * W;
-    const int yo = (int)(p % (2 * H));
-    const int b = (int)(p / (2 * H));
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + (((size_t)b * H + (yo >> 1)) * W + (xo >> 1)) * Cv + cv);
-    reinterpret_cast<uint4*>(dst)[idx] = v;
-  }
-}
-void launch_upsample2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cudaStream_t s) {
-  REQUIRE(C % 8 == 0, "upsample: C must be a multiple of 8");
-  const long long total = (long long)B * 4 * H * W * (C / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  upsample2x_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, B, H, W, C / 8);
-  CUDA_CHECK(cudaGetLastError());
-}
-
 // =============================================================================== weight packing
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin,
                                         int taps, int cin_pad, int k_off, int k_total) {
@@ -543,6 +509,40 @@ void launch_pack_conv_weight(const float* src, bf16* dst, int Cout, int Cin, int
   const long long total = (long long)Cout * taps * cin_pad;
   pack_conv_weight_kernel<<<(int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, s>>>(
       src, dst, Cout, Cin, taps, cin_pad, k_off, k_total);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Upsample(nearest 2x) + conv3x3 folded into four 2x2 convs over the low-resolution source
+// (unet.py:58-65): dst[(par*Cout + o)][t*cin_pad + c] = sum of the 3x3 taps (kh, kw) that land on
+// source offset t = (a, b) for output parity par = (py, px). Summed in fp32, rounded once.
+__global__ void pack_upfold_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin,
+                                          int cin_pad) {
+  const long long total = 4LL * Cout * 4 * cin_pad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cin_pad);
+    const int t = (int)((idx / cin_pad) % 4);
+    const int o = (int)((idx / (4LL * cin_pad)) % Cout);
+    const int par = (int)(idx / (4LL * cin_pad * Cout));
+    float v = 0.f;
+    if (c < Cin) {
+      const int py = par >> 1, px = par & 1, a = t >> 1, b = t & 1;
+      // py = 0: a = 0 <- kh {0}, a = 1 <- kh {1, 2};  py = 1: a = 0 <- kh {0, 1}, a = 1 <- kh {2}
+      const int kh0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+      const int kh1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+      const int kw0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+      const int kw1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+      const float* w = src + ((size_t)o * Cin + c) * 9;
+      for (int kh = kh0; kh <= kh1; ++kh)
+        for (int kw = kw0; kw <= kw1; ++kw) v += w[kh * 3 + kw];
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+void launch_pack_upfold_weight(const float* src, bf16* dst, int Cout, int Cin, int cin_pad, cudaStream_t s) {
+  const long long total = 4LL * Cout * 4 * cin_pad;
+  const long long blocks = (total + 255) / 256;
+  pack_upfold_weight_kernel<<<(int)(blocks > 8192 ? 8192 : blocks), 256, 0, s>>>(src, dst, Cout, Cin, cin_pad);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -5,25 +5,34 @@
 
 namespace b200sr3 {
 
-// ---- GroupNorm (unet.py:84, 117): statistics, then y = [swish]((x - mean) * rstd * gamma + beta)
+// ---- GroupNorm (unet.py:84, 117): y = [swish]((x - mean) * rstd * gamma + beta)
 // The input may be the channel concat of two tensors (unet.py:261 feeds cat((x, skip), 1) to the
-// block); groups may straddle the seam, so statistics are taken per channel and grouped after.
+// block); groups may straddle the seam, so statistics are kept per channel ("chansum": per
+// (image, channel) sum and sum of squares over the pixels) and grouped in the apply kernel.
+// chansum is produced by the conv that wrote the tensor, or by launch_chan_stats.
 struct GnPlan {
   const bf16* src0 = nullptr;   // [B,H,W,C0]
   const bf16* src1 = nullptr;   // [B,H,W,C1] or null
   int B = 0, HW = 0, C0 = 0, C1 = 0, groups = 32;
-  const float* gamma = nullptr;  // [C0+C1]
+  const float* stats0 = nullptr;  // chansum of src0 [B][C0][2]
+  const float* stats1 = nullptr;  // chansum of src1 [B][C1][2]
+  const float* gamma = nullptr;   // [C0+C1]
   const float* beta = nullptr;
-  int chunks = 1;                // CTAs per image in the statistics pass
-  float* partial = nullptr;      // [B][chunks][C][2]
-  float* scale_shift = nullptr;  // [B][C][2]: y = x*scale + shift
-  int* ticket = nullptr;         // [B], zero on entry, self-resetting
-  bf16* dst = nullptr;           // [B,H,W,C0+C1]
+  bf16* dst = nullptr;            // [B,H,W,C0+C1]
   int swish = 1;
 };
-void gn_choose_chunks(GnPlan& g);
-void launch_gn_stats(const GnPlan& g, cudaStream_t s);
 void launch_gn_apply(const GnPlan& g, cudaStream_t s);
+
+struct ChanStatsPlan {
+  const bf16* src = nullptr;     // [B,H,W,C]
+  int B = 0, HW = 0, C = 0;
+  int chunks = 1;                // CTAs per image
+  float* partial = nullptr;      // [B][chunks][C][2] (unused when chunks == 1)
+  int* ticket = nullptr;         // [B], zero on entry, self-resetting
+  float* chansum = nullptr;      // [B][C][2]
+};
+int chan_stats_chunks(int HW, int C);
+void launch_chan_stats(const ChanStatsPlan& g, cudaStream_t s);
 
 // ---- head conv (unet.py:196-197, downs.0): fp32 NCHW cond/x -> 3x3 conv -> NHWC bf16
 void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
@@ -53,13 +62,12 @@ void launch_posterior_update(const float* x, const float* eps, const float* z, f
 // ---- mid-block attention core (unet.py:123-139): softmax(Q K^T / sqrt(C)) V over HW tokens
 void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStream_t s);
 
-// ---- nearest 2x upsample (unet.py:61, nn.Upsample) NHWC
-void launch_upsample2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cudaStream_t s);
-
 // ---- weights / tables
 // OIHW fp32 -> dst[o][k_off + tap*cin_pad + c] bf16 (zero padded to cin_pad)
 void launch_pack_conv_weight(const float* src, bf16* dst, int Cout, int Cin, int taps, int cin_pad,
                              int k_off, int k_total, cudaStream_t s);
+// OIHW fp32 3x3 -> [4*Cout][4*cin_pad] bf16: the four parity 2x2 convs of a folded nearest-2x upsample
+void launch_pack_upfold_weight(const float* src, bf16* dst, int Cout, int Cin, int cin_pad, cudaStream_t s);
 // OIHW fp32 -> [tap*Cin + c][o] fp32 (head) / [o][tap][c] fp32 (tail)
 void launch_pack_head_weight(const float* src, float* dst, int Cout, int Cin, cudaStream_t s);
 void launch_pack_tail_weight(const float* src, float* dst, int OC, int Cin, cudaStream_t s);
