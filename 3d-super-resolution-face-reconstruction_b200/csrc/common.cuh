@@ -50,9 +50,15 @@ struct StepCtl {
 // ------------------------------------------------------------------------------- small helpers
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// GroupNorm partial sums travel as int64 fixed point: integer addition is exactly associative, so
+// the statistics of an image do not depend on which CTA summed which tile.
+#define STAT_FIXED_SCALE 16777216.0f
+#define STAT_FIXED_INV (1.0 / 16777216.0)
+
 struct Act {  // NHWC bf16 activation
   bf16* ptr = nullptr;
-  float* stats = nullptr;   // chansum [B][C][2]: per-(image, channel) sum and sum of squares (GroupNorm input)
+  long long* stats = nullptr;   // [B][stat_slots][C][2]: per-(image, channel) partial sums and sums of squares,
+  int stat_slots = 1;           // 2^-24 fixed point (GroupNorm input statistics; the consumer adds the slots)
   int B = 0, H = 0, W = 0, C = 0;
   size_t elems() const { return (size_t)B * H * W * C; }
 };

@@ -210,16 +210,23 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
   p.total_tiles = m_tiles * p.tiles_n;
   encode_weight_map(&p.w_map, w.w, w.k_total, w.cout * p.num_par, bn);
 
+  const int grid = std::min(p.total_tiles, g_num_sms);
+  p.seg_len = p.tiles_w * p.tiles_h * p.num_par;
   if (stats) {
     REQUIRE(conv_can_fuse_stats(out, up), "conv: statistics cannot be fused for this shape");
     REQUIRE(p.bb <= 2, "conv: internal tile shape error");
-    p.stat_chansum = stats->chansum;
+    // the most CTAs any segment is spread over (same owner formula as the kernel)
+    int need = 1;
+    const long long G = grid, T = p.total_tiles;
+    for (long long seg = 0; seg * p.seg_len < T; ++seg) {
+      const int first_cta = (int)(((seg * p.seg_len + 1) * G - 1) / T);
+      const int last_cta = (int)((((seg + 1) * p.seg_len) * G - 1) / T);
+      need = std::max(need, last_cta - first_cta + 1);
+    }
+    REQUIRE(need <= stats->slots, "conv: statistics scratch has too few slots");
     p.stat_partial = stats->partial;
-    p.stat_ticket = stats->ticket;
-    p.stat_slots = p.num_par * (p.bb == 1 ? p.tiles_h * p.tiles_w : 1);
-    REQUIRE(p.stat_slots <= stats->max_slots, "conv: statistics scratch too small");
+    p.stat_slots = stats->slots;
   }
-  const int grid = std::min(p.total_tiles, g_num_sms);
 
   Op op;
   op.name = name;
@@ -238,11 +245,16 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
 }
 
 int conv_stat_slots(const Act& out, bool upsample2x) {
+  // upper bound over every BLOCK_N choice: the fewest tiles (tiles_n = 1) give the shortest runs
   const int PH = upsample2x ? out.H / 2 : out.H, PW = upsample2x ? out.W / 2 : out.W;
   const int bw = std::min(PW, CONV_BLOCK_M);
   const int bh = std::min(PH, CONV_BLOCK_M / bw);
   const int bb = CONV_BLOCK_M / (bw * bh);
-  return (upsample2x ? 4 : 1) * (bb == 1 ? (PH / bh) * (PW / bw) : 1);
+  const int seg_len = (PH / bh) * (PW / bw) * (upsample2x ? 4 : 1);
+  const long long T = (long long)seg_len * ceil_div(out.B, bb);
+  const long long G = std::min<long long>(T, g_num_sms);
+  const long long min_run = std::max<long long>(1, T / G);
+  return (int)((seg_len - 1) / min_run + 2);
 }
 
 }  // namespace b200sr3

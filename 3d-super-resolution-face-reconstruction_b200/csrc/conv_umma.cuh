@@ -56,13 +56,16 @@ struct alignas(64) ConvParams {
   const StepCtl* ctl;
   const bf16* residual;            // same shape as out, added in the epilogue (may be null)
   bf16* out;
-  // GroupNorm statistics of the output (null: not wanted). chansum[b][c] = (sum, sumsq) over the
-  // image's pixels; tiles write partial[b][slot][c][2] and the last tile of an (image, n-tile)
-  // (ticket) adds the slots in a fixed order, so the result is deterministic.
-  float* stat_chansum;
-  float* stat_partial;
-  int* stat_ticket;                // [B * tiles_n], zero on entry, self-resetting
-  int stat_slots;                  // partial slots per image (num_par * tiles per image)
+  // GroupNorm statistics of the output (null: not wanted): stat_partial[b][slot][c] = (sum, sumsq)
+  // of the fp32 outputs over the pixels of image b that ONE CTA produced. A CTA owns a contiguous
+  // run of tiles, so an image is covered by a handful of CTAs; CTA number j (in launch order) of
+  // those writes slot j and the last one zero-fills the unused slots. No atomics, no fences: the
+  // consumer (gn_apply_kernel) adds the stat_slots slots. Sums are carried as 2^-24 fixed point in
+  // int64 (exactly associative), so the statistics do not depend on how tiles were split over
+  // CTAs - i.e. not on the batch size either: a face's result is bit-identical in any batch.
+  long long* stat_partial;
+  int stat_slots;
+  int seg_len;                     // tiles per (n tile, image[-pair]) segment = tiles_w*tiles_h*num_par
 };
 
 #ifdef __CUDACC__
@@ -201,7 +204,7 @@ struct ConvSmem {
   static constexpr int B_BYTES = BLOCK_N * CONV_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAT_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAT_BYTES = 2 * 4 * 2 * BLOCK_N * 4;         // [buf][warp][sum|sq][col] fp32
+  static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 8;             // [warp][sum|sq][col] int64 fixed point
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;            // + barriers + align slack
 };
@@ -230,16 +233,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  float* sstat = reinterpret_cast<float*>(smem_gen + S::STAT_OFFSET);
+  long long* sstat = reinterpret_cast<long long*>(smem_gen + S::STAT_OFFSET);
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the
-  // TMEM address and two "last tile of the image" flags.
+  // TMEM address.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  int* s_last = reinterpret_cast<int*>(smem_gen + S::BAR_OFFSET + 8 * (2 * STAGES + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,16 +268,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // tile -> (n tile, box origin, parity group); n varies fastest so concurrently running CTAs
-  // share the A tile in L2.
+  // A CTA owns the contiguous tile range [tile_begin, tile_end). Tile order: w fastest, then h,
+  // parity group, image(-pair), n tile - so consecutive tiles belong to the same image and share
+  // input halos in L2, and the GroupNorm partial sums of an image stay in one CTA for long runs.
+  const int tile_begin = (int)(((long long)blockIdx.x * p.total_tiles) / gridDim.x);
+  const int tile_end = (int)(((long long)(blockIdx.x + 1) * p.total_tiles) / gridDim.x);
   struct Tile { int n_tile, w0, h0, b0, par; };
   auto decode = [&](int tile) {
     Tile t;
-    t.n_tile = tile % p.tiles_n; tile /= p.tiles_n;
     t.w0 = (tile % p.tiles_w) * p.bw; tile /= p.tiles_w;
     t.h0 = (tile % p.tiles_h) * p.bh; tile /= p.tiles_h;
+    t.par = tile % p.num_par; tile /= p.num_par;
     t.b0 = (tile % p.tiles_b) * p.bb;
-    t.par = tile / p.tiles_b;
+    t.n_tile = tile / p.tiles_b;
     return t;
   };
 
@@ -284,7 +289,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       // ---------------------------------------------------------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const Tile t = decode(tile);
         const ConvTap* taps = p.taps + t.par * p.num_taps;
         const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N;
@@ -311,7 +316,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         ptx::mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -343,14 +348,17 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const int lw = row % p.bw;
     const int lh = (row / p.bw) % p.bh;
     const int lb = row / (p.bw * p.bh);
-    const bool do_stats = p.stat_chansum != nullptr;
+    const bool do_stats = p.stat_partial != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
     const int osc = p.num_par == 4 ? 2 : 1;
-    const int tiles_per_img = (p.bb == 1) ? p.tiles_h * p.tiles_w : 1;
+    // running per-channel (sum, sumsq) of this warp's rows: sacc[warp][sum|sq][col], lane-private
+    long long* sacc = sstat + wq * (2 * BLOCK_N);
+    if (do_stats)
+      for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const Tile t = decode(tile);
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -361,7 +369,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                          (size_t)(w * osc + (t.par & 1));
       bf16* out_row = p.out + pix * p.Cout + n0;
       const bf16* res_row = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-      float* sb = sstat + buf * (4 * 2 * BLOCK_N);
 
       ptx::mbar_wait(tmem_full_bar(buf), use & 1u);
       ptx::tc_fence_after();
@@ -403,8 +410,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
           const float s_sum = warp_transpose_sum(f, lane);
           const float s_sq = warp_transpose_sum(q, lane);
-          sb[(wq * 2 + 0) * BLOCK_N + c0 + lane] = s_sum;
-          sb[(wq * 2 + 1) * BLOCK_N + c0 + lane] = s_sq;
+          sacc[c0 + lane] += __float2ll_rn(s_sum * STAT_FIXED_SCALE);
+          sacc[BLOCK_N + c0 + lane] += __float2ll_rn(s_sq * STAT_FIXED_SCALE);
         }
       }
       // all of this thread's TMEM reads have completed: hand the accumulator back to the MMA warp
@@ -412,50 +419,32 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       ptx::mbar_arrive(tmem_empty_bar(buf));
 
       if (do_stats) {
-        epi_bar_sync();
-        const int nimg = p.bb >= 2 ? 2 : 1;       // host guarantees bb <= 2 when stats are fused
-        const int wpi = 4 / nimg;
-        const int slot = t.par * tiles_per_img + ((p.bb == 1) ? (t.h0 / p.bh) * p.tiles_w + t.w0 / p.bw : 0);
-        for (int item = tid_e; item < nimg * 2 * BLOCK_N; item += 128) {
-          const int col = item % BLOCK_N;
-          const int st = (item / BLOCK_N) & 1;
-          const int ib = item / (2 * BLOCK_N);
-          float a = 0.f;
-          for (int ww = 0; ww < wpi; ++ww) a += sb[((ib * wpi + ww) * 2 + st) * BLOCK_N + col];
-          const int bi = t.b0 + ib;
-          if (bi < p.B) {
-            const size_t ch = (size_t)(n0 + col);
-            if (p.stat_slots == 1) p.stat_chansum[((size_t)bi * p.Cout + ch) * 2 + st] = a;
-            else p.stat_partial[(((size_t)bi * p.stat_slots + slot) * p.Cout + ch) * 2 + st] = a;
-          }
-        }
-        if (p.stat_slots > 1) {
-          __threadfence();
+        const int seg = tile / p.seg_len;
+        if (tile + 1 == tile_end || (tile + 1) / p.seg_len != seg) {
+          // ---- the CTA's run over this (n tile, image[-pair]) segment ends: publish its partial sums
+          const long long G = gridDim.x, T = p.total_tiles;
+          const int first_cta = (int)((((long long)seg * p.seg_len + 1) * G - 1) / T);
+          const int last_cta = (int)((((long long)(seg + 1) * p.seg_len) * G - 1) / T);
+          const int slot = (int)blockIdx.x - first_cta;
+          const int nimg = p.bb >= 2 ? 2 : 1;       // host guarantees bb <= 2 when stats are fused
+          const int wpi = 4 / nimg;
           epi_bar_sync();
-          if (tid_e < 2) {
-            int last = 0;
-            const int bi = t.b0 + tid_e;
-            if (tid_e < nimg && bi < p.B) {
-              int* tk = p.stat_ticket + bi * p.tiles_n + t.n_tile;
-              last = (atomicAdd(tk, 1) == p.stat_slots - 1);
-              if (last) *tk = 0;
-            }
-            s_last[tid_e] = last;
-          }
-          epi_bar_sync();
-          for (int ib = 0; ib < nimg; ++ib) {
-            if (!s_last[ib]) continue;
-            __threadfence();
+          for (int item = tid_e; item < nimg * 2 * BLOCK_N; item += 128) {
+            const int col = item % BLOCK_N;
+            const int st = (item / BLOCK_N) & 1;
+            const int ib = item / (2 * BLOCK_N);
+            long long a = 0;
+            for (int ww = 0; ww < wpi; ++ww) a += sstat[((ib * wpi + ww) * 2 + st) * BLOCK_N + col];
             const int bi = t.b0 + ib;
-            for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
-              // item = col*2 + st: consecutive threads read consecutive floats of a slot row
-              const size_t off = (size_t)n0 * 2 + item;
-              const float* src = p.stat_partial + (size_t)bi * p.stat_slots * p.Cout * 2 + off;
-              float a = 0.f;
-              for (int sl = 0; sl < p.stat_slots; ++sl) a += __ldcg(src + (size_t)sl * p.Cout * 2);
-              p.stat_chansum[(size_t)bi * p.Cout * 2 + off] = a;
+            if (bi < p.B) {
+              long long* dst = p.stat_partial + (((size_t)bi * p.stat_slots + slot) * p.Cout + (n0 + col)) * 2 + st;
+              *dst = a;
+              if ((int)blockIdx.x == last_cta)
+                for (int sl = slot + 1; sl < p.stat_slots; ++sl) dst[(size_t)(sl - slot) * p.Cout * 2] = 0;
             }
           }
+          epi_bar_sync();
+          for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
         }
       }
     }

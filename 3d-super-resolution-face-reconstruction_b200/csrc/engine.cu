@@ -74,6 +74,7 @@ Engine::Engine(const b200sr3_config& cfg, int device) : cfg_(cfg), device_(devic
   CUDA_CHECK(cudaMemset(ctl_, 0, sizeof(StepCtl)));
   if (const char* g = getenv("B200SR3_NO_GRAPH")) use_graph_ = !(g[0] == '1');
   if (const char* g = getenv("B200SR3_BLOCK_N")) force_block_n_ = atoi(g);
+  if (const char* g = getenv("B200SR3_NO_FUSED_STATS")) fuse_stats_ = !(g[0] == '1');
   build_layers();
 }
 
@@ -391,11 +392,12 @@ void Engine::build_workspace(Workspace& ws) {
     ws.bytes += bytes;
     return p;
   };
-  auto act = [&](int H, int W, int C) {
+  auto act = [&](int H, int W, int C, int stat_slots = 1) {
     Act a;
     a.B = B; a.H = H; a.W = W; a.C = C;
     a.ptr = (bf16*)dalloc(a.elems() * sizeof(bf16));
-    a.stats = (float*)dalloc((size_t)B * C * 2 * sizeof(float));
+    a.stat_slots = stat_slots;
+    a.stats = (long long*)dalloc((size_t)B * stat_slots * C * 2 * sizeof(long long));
     return a;
   };
   const int oc = cfg_.out_channel;
@@ -423,8 +425,9 @@ void Engine::build_workspace(Workspace& ws) {
   // GroupNorm (+Swish) of [x0 | x1] into a fresh tensor (one HBM pass; statistics come with the inputs)
   auto group_norm = [&](const std::string& name, const Act& x0, const Act* x1, const std::string& gkey, bool swish) {
     auto g = std::make_shared<GnPlan>();
-    g->src0 = x0.ptr; g->C0 = x0.C; g->stats0 = x0.stats;
+    g->src0 = x0.ptr; g->C0 = x0.C; g->stats0 = x0.stats; g->slots0 = x0.stat_slots;
     g->src1 = x1 ? x1->ptr : nullptr; g->C1 = x1 ? x1->C : 0; g->stats1 = x1 ? x1->stats : nullptr;
+    g->slots1 = x1 ? x1->stat_slots : 1;
     g->B = B; g->HW = x0.H * x0.W; g->groups = G;
     const int C = g->C0 + g->C1;
     REQUIRE(C % G == 0, "GroupNorm: channels not divisible by norm_groups");
@@ -440,21 +443,15 @@ void Engine::build_workspace(Workspace& ws) {
   auto conv = [&](const std::string& name, const Act& src, int taps, int stride, bool up, const PackedConv& w,
                   const Act* r0, const Act* r1, const float* bias, int bias_stride, const bf16* residual,
                   int Ho, int Wo, bool want_stats) {
-    Act y = act(Ho, Wo, w.cout);
+    Act probe;
+    probe.B = B; probe.H = Ho; probe.W = Wo; probe.C = w.cout;
+    const bool fuse = want_stats && fuse_stats_ && conv_can_fuse_stats(probe, up);
+    Act y = act(Ho, Wo, w.cout, fuse ? conv_stat_slots(probe, up) : 1);
     ConvSource cs;
     cs.act = src; cs.taps = taps; cs.stride = stride; cs.upsample2x = up;
     ConvStats st;
-    const bool fuse = want_stats && conv_can_fuse_stats(y, up);
-    if (fuse) {
-      st.chansum = y.stats;
-      st.max_slots = conv_stat_slots(y, up);
-      if (st.max_slots > 1) {
-        st.partial = (float*)dalloc((size_t)B * st.max_slots * w.cout * 2 * sizeof(float));
-        const size_t nt = (size_t)B * (w.cout / 64);
-        st.ticket = (int*)dalloc(nt * sizeof(int));
-        CUDA_CHECK(cudaMemset(st.ticket, 0, nt * sizeof(int)));
-      }
-    }
+    st.partial = y.stats;
+    st.slots = y.stat_slots;
     ws.ops.push_back(make_conv_op(name, cs, r0, r1, w, bias, bias_stride, ctl_, residual, y, force_block_n_,
                                   fuse ? &st : nullptr));
     ws.n_conv++;

@@ -131,6 +131,7 @@ class Engine {
   cudaStream_t capture_stream_ = nullptr;
   bool use_graph_ = true;
   int force_block_n_ = 0;
+  bool fuse_stats_ = true;     // B200SR3_NO_FUSED_STATS=1: GroupNorm statistics by chan_stats_kernel instead
 
   std::map<std::pair<int, int>, std::unique_ptr<Workspace>> workspaces_;
 };
@@ -143,10 +144,8 @@ struct ConvSource {
   bool upsample2x = false;   // the conv reads nearest-2x(act) (unet.py:58-65), folded into 4 parity convs
 };
 struct ConvStats {    // where the epilogue leaves the GroupNorm statistics of the output
-  float* chansum = nullptr;   // [B][Cout][2]
-  float* partial = nullptr;   // [B][max_slots][Cout][2]
-  int* ticket = nullptr;      // [B * Cout/64] zeroed
-  int max_slots = 0;
+  long long* partial = nullptr;   // [B][slots][Cout][2], 2^-24 fixed point
+  int slots = 0;
 };
 bool conv_can_fuse_stats(const Act& out, bool upsample2x);
 int conv_stat_slots(const Act& out, bool upsample2x);

@@ -62,13 +62,14 @@ __global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g)
   for (int i = 0; i < 8; ++i) { red[tid * 16 + i] = s[i]; red[tid * 16 + 8 + i] = q[i]; }
   __syncthreads();
   // reduce over rows: thread (j < Cv*16) owns one (channel-vector, slot) pair
-  float* out = (g.chunks == 1) ? g.chansum + (size_t)b * C * 2 : g.partial + (size_t)(b * g.chunks + chunk) * C * 2;
   for (int j = tid; j < Cv * 16; j += GN_THREADS) {
     const int v = j >> 4, slot = j & 15;
     float a = 0.f;
     for (int rr = 0; rr < rows; ++rr) a += red[(rr * Cv + v) * 16 + slot];
     // layout [c][2] with slot<8 -> sum of channel v*8+slot, else sumsq
-    out[(size_t)(v * 8 + (slot & 7)) * 2 + (slot >> 3)] = a;
+    const size_t o = (size_t)(v * 8 + (slot & 7)) * 2 + (slot >> 3);
+    if (g.chunks == 1) g.chansum[(size_t)b * C * 2 + o] = __float2ll_rn(a * STAT_FIXED_SCALE);
+    else g.partial[(size_t)(b * g.chunks + chunk) * C * 2 + o] = a;
   }
   if (g.chunks == 1) return;
   __threadfence();
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g)
   for (int j = tid; j < C * 2; j += GN_THREADS) {
     float a = 0.f;
     for (int k = 0; k < g.chunks; ++k) a += __ldcg(g.partial + (size_t)(b * g.chunks + k) * C * 2 + j);
-    g.chansum[(size_t)b * C * 2 + j] = a;
+    g.chansum[(size_t)b * C * 2 + j] = __float2ll_rn(a * STAT_FIXED_SCALE);
   }
   if (tid == 0) g.ticket[b] = 0;
 }
@@ -97,10 +98,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int appl
   const int cv = tid % Cv, r = tid / Cv;
   const int b = blockIdx.y;
   for (int c = tid; c < C; c += GN_THREADS) {
-    const float2 v = (c < g.C0) ? *reinterpret_cast<const float2*>(g.stats0 + ((size_t)b * g.C0 + c) * 2)
-                                : *reinterpret_cast<const float2*>(g.stats1 + ((size_t)b * g.C1 + (c - g.C0)) * 2);
-    chan[2 * c] = v.x;
-    chan[2 * c + 1] = v.y;
+    // add the producers' partial-sum slots in a fixed order
+    const long long* sp;
+    int ns, cs;
+    if (c < g.C0) { sp = g.stats0 + ((size_t)b * g.slots0 * g.C0 + c) * 2; ns = g.slots0; cs = g.C0; }
+    else { sp = g.stats1 + ((size_t)b * g.slots1 * g.C1 + (c - g.C0)) * 2; ns = g.slots1; cs = g.C1; }
+    long long a = 0, d = 0;
+    for (int k = 0; k < ns; ++k) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(sp + (size_t)k * cs * 2);
+      a += v.x;
+      d += v.y;
+    }
+    chan[2 * c] = (float)((double)a * STAT_FIXED_INV);
+    chan[2 * c + 1] = (float)((double)d * STAT_FIXED_INV);
   }
   __syncthreads();
   const int cg = C / g.groups;

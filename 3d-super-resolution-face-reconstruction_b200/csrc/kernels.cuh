@@ -14,8 +14,9 @@ struct GnPlan {
   const bf16* src0 = nullptr;   // [B,H,W,C0]
   const bf16* src1 = nullptr;   // [B,H,W,C1] or null
   int B = 0, HW = 0, C0 = 0, C1 = 0, groups = 32;
-  const float* stats0 = nullptr;  // chansum of src0 [B][C0][2]
-  const float* stats1 = nullptr;  // chansum of src1 [B][C1][2]
+  const long long* stats0 = nullptr;  // partial sums of src0 [B][slots0][C0][2], 2^-24 fixed point
+  const long long* stats1 = nullptr;  // partial sums of src1 [B][slots1][C1][2]
+  int slots0 = 1, slots1 = 1;
   const float* gamma = nullptr;   // [C0+C1]
   const float* beta = nullptr;
   bf16* dst = nullptr;            // [B,H,W,C0+C1]
@@ -29,7 +30,7 @@ struct ChanStatsPlan {
   int chunks = 1;                // CTAs per image
   float* partial = nullptr;      // [B][chunks][C][2] (unused when chunks == 1)
   int* ticket = nullptr;         // [B], zero on entry, self-resetting
-  float* chansum = nullptr;      // [B][C][2]
+  long long* chansum = nullptr;  // [B][C][2], 2^-24 fixed point (one slot)
 };
 int chan_stats_chunks(int HW, int C);
 void launch_chan_stats(const ChanStatsPlan& g, cudaStream_t s);
