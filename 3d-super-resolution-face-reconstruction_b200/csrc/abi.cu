@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/b200sr3.h. Exceptions never cross the boundary: they
 // are turned into a non-zero return code plus a thread-local message.
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -200,7 +201,23 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
     cs.act = src; cs.taps = taps; cs.stride = stride; cs.upsample2x = upsample2x != 0;
     int force_bn = 0;
     if (const char* g = getenv("B200SR3_BLOCK_N")) force_bn = atoi(g);
-    Op op = make_conv_op("conv2d", cs, nullptr, nullptr, pc, bias, 0, nullptr, res, out, force_bn, nullptr);
+    // measurement switches: B200SR3_CONV2D_STATS=1 fuses the GroupNorm statistics into the epilogue
+    // (as the engine does); B200SR3_CONV_TIMING=1 prints per-role cycle counters of the last launch.
+    ConvStats st;
+    const char* ev = getenv("B200SR3_CONV2D_STATS");
+    const bool want_stats = ev && ev[0] == '1' && conv_can_fuse_stats(out, upsample2x != 0);
+    if (want_stats) {
+      st.slots = conv_stat_slots(out, upsample2x != 0);
+      st.partial = (long long*)dalloc((size_t)B * st.slots * Cout * 2 * sizeof(long long));
+    }
+    ev = getenv("B200SR3_CONV_TIMING");
+    const bool timing = ev && ev[0] == '1';
+    if (timing) {
+      st.dbg = (unsigned long long*)dalloc(256 * 8 * sizeof(unsigned long long));
+      CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 8 * sizeof(unsigned long long)));
+    }
+    Op op = make_conv_op("conv2d", cs, nullptr, nullptr, pc, bias, 0, nullptr, res, out, force_bn,
+                         (want_stats || timing) ? &st : nullptr);
     op.run(s);
     launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -217,6 +234,25 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
       *avg_ms = ms / iters;
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);
+    }
+    if (timing) {
+      std::vector<unsigned long long> h(256 * 8);
+      CUDA_CHECK(cudaMemcpy(h.data(), st.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      double acc[8] = {0};
+      int n = 0;
+      for (int c = 0; c < 256; ++c) {
+        if (h[c * 8 + 6] == 0) continue;
+        ++n;
+        for (int k = 0; k < 8; ++k) acc[k] += (double)h[c * 8 + k];
+      }
+      if (n) {
+        const double tiles = acc[6] / n;
+        fprintf(stderr,
+                "conv timing (avg over %d CTAs, %.1f tiles each, cycles per tile): producer waits empty %.0f | "
+                "mma waits full %.0f, waits tmem %.0f | epilogue waits accum %.0f, total %.0f\n",
+                n, tiles, acc[0] / n / tiles, acc[2] / n / tiles, acc[3] / n / tiles, acc[4] / n / tiles,
+                acc[5] / n / tiles);
+      }
     }
   });
 }

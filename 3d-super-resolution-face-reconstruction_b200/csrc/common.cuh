@@ -64,7 +64,9 @@ struct Act {  // NHWC bf16 activation
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (both ~2^-22 relative: far below the bf16
+// rounding of the stored result); the IEEE division this replaces cost ~15 instructions.
+__device__ __forceinline__ float swish_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);

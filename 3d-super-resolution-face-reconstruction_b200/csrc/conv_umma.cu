@@ -55,9 +55,9 @@ static void encode_weight_map(CUtensorMap* m, const bf16* w, int k_total, int co
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-template <int BN, int ST>
+template <int BN, int ST, int MW>
 static void launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
-  conv_umma_kernel<BN, ST><<<grid, CONV_THREADS, ConvSmem<BN, ST>::TOTAL, s>>>(p);
+  conv_umma_kernel<BN, ST, MW><<<grid, CONV_THREADS, ConvSmem<BN, ST>::TOTAL, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -66,11 +66,11 @@ constexpr int ST64 = 8, ST128 = 6, ST256 = 4;
 static int g_num_sms = 148;
 
 void conv_init_device() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64, ST64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64, ST64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ConvSmem<64, ST64>::TOTAL));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128, ST128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128, ST128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ConvSmem<128, ST128>::TOTAL));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256, ST256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256, ST256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ConvSmem<256, ST256>::TOTAL));
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -198,7 +198,10 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
     const int cand[3] = {256, 128, 64};
     for (int c : cand) {
       if (out.C % c != 0) continue;
-      const double per_kb = std::max(2.0 * c, (16384.0 + 128.0 * c) / 64.0);
+      // tensor time per K block (measured: 128 cycles per N=256 MMA; with two issuing warps 64 per
+      // N=128 and ~48 per N=64 MMA) vs operand bytes at ~96 B/cycle/SM from L2
+      const double mma = c == 256 ? 512.0 : (c == 128 ? 256.0 : 192.0);
+      const double per_kb = std::max(mma, (16384.0 + 128.0 * c) / 96.0);
       const double rounds = (double)ceil_div(m_tiles * (out.C / c), g_num_sms);
       const double cost = rounds * (kblocks * per_kb + 400.0 + 6.0 * c);
       if (cost < best) { best = cost; bn = c; }
@@ -212,7 +215,9 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
 
   const int grid = std::min(p.total_tiles, g_num_sms);
   p.seg_len = p.tiles_w * p.tiles_h * p.num_par;
-  if (stats) {
+  if (stats) p.dbg = stats->dbg;
+  if (const char* ab = getenv("B200SR3_CONV_ABLATE")) p.ablate = atoi(ab);
+  if (stats && stats->partial) {
     REQUIRE(conv_can_fuse_stats(out, up), "conv: statistics cannot be fused for this shape");
     REQUIRE(p.bb <= 2, "conv: internal tile shape error");
     // the most CTAs any segment is spread over (same owner formula as the kernel)
@@ -237,9 +242,9 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
     op.flops = 2.0 * m * (double)out.C * k;     // reference graph (full-resolution 3x3 for Upsample)
   }
   op.run = [pp, grid, bn](cudaStream_t s) {
-    if (bn == 256) launch_conv<256, ST256>(*pp, grid, s);
-    else if (bn == 128) launch_conv<128, ST128>(*pp, grid, s);
-    else launch_conv<64, ST64>(*pp, grid, s);
+    if (bn == 256) launch_conv<256, ST256, 1>(*pp, grid, s);
+    else if (bn == 128) launch_conv<128, ST128, 2>(*pp, grid, s);
+    else launch_conv<64, ST64, 2>(*pp, grid, s);
   };
   return op;
 }

@@ -66,6 +66,11 @@ struct alignas(64) ConvParams {
   long long* stat_partial;
   int stat_slots;
   int seg_len;                     // tiles per (n tile, image[-pair]) segment = tiles_w*tiles_h*num_par
+  // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv2d): [grid][8] cycle counters
+  unsigned long long* dbg;
+  // ablation switches for tools/conv_bench.py (B200SR3_CONV_ABLATE bit mask; results are then wrong):
+  // 1 = no global stores, 2 = no A loads, 4 = no W loads, 8 = no bias/residual loads, 16 = no TMEM loads
+  int ablate;
 };
 
 #ifdef __CUDACC__
@@ -98,6 +103,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe of a phase (used to look one pipeline stage ahead).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trap (-> cudaErrorLaunchFailure), never as a
 // hung GPU. ~2 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -110,6 +127,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// One lane of a fully converged warp. Unlike `lane == 0`, the compiler knows exactly one thread is
+// active under this predicate, so tcgen05 / TMA operands stay in uniform registers (no per-lane
+// serialisation loop around every UTCHMMA / UTMALDG).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -226,22 +251,37 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BLOCK_N, int STAGES>
+// role timing helpers (two accumulators per thread; only when p.dbg is set)
+#define DBG_DECL() unsigned long long dbg_acc[2] = {0ull, 0ull}; long long dbg_t0 = 0
+#define DBG_T0() do { if (p.dbg) dbg_t0 = clock64(); } while (0)
+#define DBG_ACC(i) do { if (p.dbg) dbg_acc[i] += (unsigned long long)(clock64() - dbg_t0); } while (0)
+#define DBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 8 + (slot) + _i] = dbg_acc[_i]; } while (0)
+
+// MMA_WARPS: a single warp can issue one tcgen05.mma per ~86 cycles (measured, tools/micro/
+// umma_rate*.cu), which only saturates the tensor pipe at N = 256 (128 cycles each). For N <= 128 two
+// warps issue concurrently, each into its own accumulators and from its own half of the smem ring
+// (stage s belongs to warp s % MMA_WARPS): tiles alternate between the warps, the producer
+// interleaves their K blocks. Measured: N = 128 reaches the full 4096 MAC/cycle/SM this way.
+template <int BLOCK_N, int STAGES, int MMA_WARPS>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(MMA_WARPS == 1 || MMA_WARPS == 2, "one or two MMA warps");
+  static_assert(STAGES % MMA_WARPS == 0 && 2 * MMA_WARPS * BLOCK_N <= 512, "ring / TMEM budget");
+  constexpr int NBUF = 2 * MMA_WARPS;       // TMEM accumulators (two per MMA warp)
+  constexpr int RING = STAGES / MMA_WARPS;  // smem stages per MMA warp
   using S = ConvSmem<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   long long* sstat = reinterpret_cast<long long*>(smem_gen + S::STAT_OFFSET);
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the
-  // TMEM address.
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[NBUF], tmem_empty[NBUF]; then
+  // the TMEM address.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
-  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + NBUF + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,13 +295,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       ptx::mbar_init(tmem_full_bar(b), 1);
       ptx::mbar_init(tmem_empty_bar(b), 128);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  if (warp == 3) ptx::tmem_alloc(tmem_slot, NBUF * BLOCK_N);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -285,60 +325,107 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       // ---------------------------------------------------------------- TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const Tile t = decode(tile);
-        const ConvTap* taps = p.taps + t.par * p.num_taps;
-        const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N;
+      // Tiles are taken MMA_WARPS at a time; their K blocks are interleaved so that every MMA warp's
+      // ring fills at the same pace. Ring j uses stages j, j + MMA_WARPS, ...
+      int rs[MMA_WARPS];          // next ring-local stage
+      uint32_t rphase[MMA_WARPS];
+#pragma unroll
+      for (int j = 0; j < MMA_WARPS; ++j) { rs[j] = 0; rphase[j] = 0; }
+      DBG_DECL();
+      for (int tile0 = tile_begin; tile0 < tile_end; tile0 += MMA_WARPS) {
+        Tile t[MMA_WARPS];
+#pragma unroll
+        for (int j = 0; j < MMA_WARPS; ++j) t[j] = decode(min(tile0 + j, tile_end - 1));
         int kb = 0;
         for (int ti = 0; ti < p.num_taps; ++ti) {
-          const ConvTap tap = taps[ti];
-          const CUtensorMap* amap = &p.a_map[tap.map];
-          for (int cb = 0; cb < tap.cblocks; ++cb, ++kb) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
-            const uint32_t sb = sa + S::A_BYTES;
-            ptx::mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-            ptx::tma_load_4d(sa, amap, full_bar(stage), cb * CONV_BLOCK_K, t.w0 + tap.dw, t.h0 + tap.dh, t.b0);
-            ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K, wrow);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          const int cblocks = p.taps[ti].cblocks;      // identical in every parity group
+          for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+#pragma unroll
+            for (int j = 0; j < MMA_WARPS; ++j) {
+              if (tile0 + j >= tile_end) continue;
+              const ConvTap tap = p.taps[t[j].par * p.num_taps + ti];
+              const int stage = rs[j] * MMA_WARPS + j;
+              DBG_T0();
+              ptx::mbar_wait(empty_bar(stage), rphase[j] ^ 1u);
+              DBG_ACC(0);
+              const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+              const uint32_t sb = sa + S::A_BYTES;
+              ptx::mbar_expect_tx(full_bar(stage), ((p.ablate & 2) ? 0 : S::A_BYTES) + ((p.ablate & 4) ? 0 : S::B_BYTES));
+              if (!(p.ablate & 2))
+                ptx::tma_load_4d(sa, &p.a_map[tap.map], full_bar(stage), cb * CONV_BLOCK_K, t[j].w0 + tap.dw,
+                                 t[j].h0 + tap.dh, t[j].b0);
+              if (!(p.ablate & 4))
+                ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K,
+                                 t[j].par * p.Cout + t[j].n_tile * BLOCK_N);
+              if (++rs[j] == RING) { rs[j] = 0; rphase[j] ^= 1u; }
+            }
           }
         }
       }
+      DBG_FLUSH(0, 1);
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+  } else if (warp <= MMA_WARPS) {
+    {
+      // ---------------------------------------------------------------- MMA issuer(s)
+      // The whole warp walks the loop (all values are warp-uniform); one elected lane issues.
+      const int mw = warp - 1;                  // this warp takes tiles tile_begin + mw, + MMA_WARPS, ...
       const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M, BLOCK_N);
-      int stage = 0;
+      int lstage = 0;                           // ring-local stage
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
+      int it = mw;
+      bool ready = false;
+      DBG_DECL();
+      for (int tile = tile_begin + mw; tile < tile_end; tile += MMA_WARPS, it += MMA_WARPS) {
+        const int buf = it % NBUF;
+        const uint32_t use = (uint32_t)(it / NBUF);
+        DBG_T0();
         ptx::mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+        DBG_ACC(1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+          const int stage = lstage * MMA_WARPS + mw;
+          DBG_T0();
+          if (!ready) ptx::mbar_wait(full_bar(stage), phase);
+          DBG_ACC(0);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
           const uint32_t sb = sa + S::A_BYTES;
+          const bool elected = ptx::elect_one();
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < CONV_BLOCK_K / 16; ++k) {
-            // advancing 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in the address field
-            const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
-            const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
-            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 2; ++k) {
+              // advancing 16 bf16 (32 B) along K inside the 128 B swizzle row: +2 in the address field
+              const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
+              const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
+              ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          // Whatever this warp does between the last MMA of one stage and the first of the next is
+          // exposed (issue is in order), so probe the NEXT stage's barrier now, while two MMAs are
+          // in flight, and skip the blocking wait at the top of the loop when it has landed.
+          const int nl = (lstage + 1 == RING) ? 0 : lstage + 1;
+          const uint32_t nphase = (lstage + 1 == RING) ? (phase ^ 1u) : phase;
+          const bool more = (kb + 1 < p.num_kblocks) || (tile + MMA_WARPS < tile_end);
+          ready = more && __all_sync(0xffffffffu, ptx::mbar_test_wait(full_bar(nl * MMA_WARPS + mw), nphase));
+          if (elected) {
+#pragma unroll
+            for (int k = 2; k < 4; ++k) {
+              const uint64_t da = ptx::make_sw128_desc(sa + k * 32);
+              const uint64_t db = ptx::make_sw128_desc(sb + k * 32);
+              ptx::umma_bf16(d_tmem, da, db, idesc, 1u);
+            }
+            ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+            if (kb == p.num_kblocks - 1) ptx::umma_commit(tmem_full_bar(buf));   // accumulator complete
+          }
+          __syncwarp();
+          lstage = nl;
+          phase = nphase;
         }
-        ptx::umma_commit(tmem_full_bar(buf));   // accumulator complete
       }
+      if (lane == 0 && mw == 0) DBG_FLUSH(2, 2);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -358,10 +445,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
 
     int it = 0;
+    DBG_DECL();
+    const long long dbg_start = p.dbg ? clock64() : 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const Tile t = decode(tile);
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const int buf = it % NBUF;
+      const uint32_t use = (uint32_t)(it / NBUF);
       const int n0 = t.n_tile * BLOCK_N;
       const int b = t.b0 + lb, h = t.h0 + lh, w = t.w0 + lw;
       const bool valid = (b < p.B) && (h < p.Hout) && (w < p.Wout);
@@ -370,18 +459,25 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       bf16* out_row = p.out + pix * p.Cout + n0;
       const bf16* res_row = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
 
+      DBG_T0();
       ptx::mbar_wait(tmem_full_bar(buf), use & 1u);
+      DBG_ACC(0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
-        ptx::tmem_ld32(taddr + (uint32_t)c0, v);
-        ptx::tmem_ld_wait();
+        if (!(p.ablate & 16)) {
+          ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(c0 + j);
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
+        if (bias && !(p.ablate & 8)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
@@ -389,7 +485,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
         }
         if (valid) {
-          if (res_row) {
+          if (res_row && !(p.ablate & 8)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float r[8];
@@ -398,8 +494,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               for (int e = 0; e < 8; ++e) f[j + e] += r[e];
             }
           }
+          if (!(p.ablate & 1)) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
+            for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
+          }
         }
         if (do_stats) {
           float q[32];
@@ -448,11 +546,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
       }
     }
+    if (p.dbg && tid_e == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = dbg_acc[0];                      // epilogue: waiting for an accumulator
+      p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - dbg_start);   // epilogue: total
+      p.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(tile_end - tile_begin);
+    }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if (warp == 3) ptx::tmem_dealloc(tmem_base, NBUF * BLOCK_N);
 }
 #endif  // __CUDACC__
 

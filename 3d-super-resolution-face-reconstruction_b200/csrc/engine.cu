@@ -470,10 +470,11 @@ void Engine::build_workspace(Workspace& ws) {
         const float *xw = ws.x, *hw = head_w_, *hb = T_(l.name + ".bias");
         bf16* dst = cur.ptr;
         const int co = l.cout;
+        long long* hstats = (fuse_stats_ && head_conv_fast_path(cc + oc, R, co)) ? cur.stats : nullptr;
         ws.ops.push_back(Op{l.name, false, [=](cudaStream_t s) {
-          launch_head_conv(cond, xw, cc, oc, hw, hb, B, R, co, dst, s);
+          launch_head_conv(cond, xw, cc, oc, hw, hb, B, R, co, dst, hstats, s);
         }});
-        chan_stats(l.name, cur);
+        if (!hstats) chan_stats(l.name, cur);
         feats.push_back(cur);
         break;
       }

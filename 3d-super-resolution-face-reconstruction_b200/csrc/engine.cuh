@@ -146,6 +146,7 @@ struct ConvSource {
 struct ConvStats {    // where the epilogue leaves the GroupNorm statistics of the output
   long long* partial = nullptr;   // [B][slots][Cout][2], 2^-24 fixed point
   int slots = 0;
+  unsigned long long* dbg = nullptr;   // role timing counters [148][8] (measurement only)
 };
 bool conv_can_fuse_stats(const Act& out, bool upsample2x);
 int conv_stat_slots(const Act& out, bool upsample2x);

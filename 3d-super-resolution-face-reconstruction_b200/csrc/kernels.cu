@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g)
 
 // y = [swish]((x - mean_g) * rstd_g * gamma + beta) over [src0 | src1]; grid (apply_chunks, B):
 // a CTA forms the group statistics of its image from chansum, then streams a pixel range.
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(GnPlan g, int apply_chunks) {
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(GnPlan g, int apply_chunks) {
   __shared__ float chan[1024 * 2];
   __shared__ float gstat[64 * 2];
   const int C = g.C0 + g.C1;
@@ -233,8 +233,120 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   *reinterpret_cast<uint4*>(out + pix * Cout + cgp * 8) = pack8(acc);
 }
 
+// Fast path (Cout = 64, R % 32 == 0): a CTA owns an 8 x 32 pixel tile, one pixel per thread with all
+// 64 output channels in registers; the input tile (+halo) and the [K][64] weights sit in shared
+// memory (weights are read as warp-wide broadcasts). A warp is one tile row, so the per-channel
+// (sum, sumsq) of the fp32 outputs reduce with the same shuffle transpose the tcgen05 epilogue
+// uses and leave the CTA as 128 int64 fixed-point atomics (exactly associative -> deterministic).
+constexpr int HEAD_TW = 32, HEAD_TH = 8;
+
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float keep = upper ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(HEAD_TW * HEAD_TH, 2)
+head_conv64_kernel(const float* __restrict__ cond, const float* __restrict__ x, int c_cond, int c_x,
+                   const float* __restrict__ w_kc, const float* __restrict__ bias, int B, int R,
+                   bf16* __restrict__ out, unsigned long long* __restrict__ stats) {
+  constexpr int COUT = 64;
+  extern __shared__ float hs[];
+  const int Cin = c_cond + c_x;
+  const int K = Cin * 9;
+  float* w_s = hs;                                  // [K][64]
+  float* in_s = hs + K * COUT;                      // [Cin][TH+2][TW+2]
+  __shared__ unsigned long long sred[2 * COUT];
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int tiles_x = R / HEAD_TW, tiles_y = R / HEAD_TH;
+  int tile = blockIdx.x;
+  const int x0 = (tile % tiles_x) * HEAD_TW; tile /= tiles_x;
+  const int y0 = (tile % tiles_y) * HEAD_TH;
+  const int b = tile / tiles_y;
+
+  for (int i = tid; i < K * COUT / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w_kc) + i);
+  if (tid < 2 * COUT) sred[tid] = 0ull;
+  constexpr int IW = HEAD_TW + 2, IH = HEAD_TH + 2;
+  for (int i = tid; i < Cin * IH * IW; i += blockDim.x) {
+    const int ix = i % IW, iy = (i / IW) % IH, ci = i / (IW * IH);
+    const int gx = x0 + ix - 1, gy = y0 + iy - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < R && gy >= 0 && gy < R)
+      v = (ci < c_cond) ? __ldg(cond + (((size_t)b * c_cond + ci) * R + gy) * R + gx)
+                        : __ldg(x + (((size_t)b * c_x + (ci - c_cond)) * R + gy) * R + gx);
+    in_s[i] = v;
+  }
+  __syncthreads();
+
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; j += 4) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
+    acc[j] = bv.x; acc[j + 1] = bv.y; acc[j + 2] = bv.z; acc[j + 3] = bv.w;
+  }
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = in_s[(ci * IH + ty + ky) * IW + tx + kx];
+      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * Cin + ci) * COUT);
+#pragma unroll
+      for (int j = 0; j < COUT / 4; ++j) {
+        const float4 w = wr[j];
+        acc[4 * j] = fmaf(v, w.x, acc[4 * j]);
+        acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+      }
+    }
+  }
+  bf16* dst = out + (((size_t)b * R + y0 + ty) * R + x0 + tx) * COUT;
+#pragma unroll
+  for (int j = 0; j < COUT; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(acc + j);
+
+  if (stats) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float f[32], q[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { f[j] = acc[half * 32 + j]; q[j] = f[j] * f[j]; }
+      const float s_sum = warp_transpose_sum32(f, tx);
+      const float s_sq = warp_transpose_sum32(q, tx);
+      atomicAdd(&sred[(half * 32 + tx) * 2], (unsigned long long)__float2ll_rn(s_sum * STAT_FIXED_SCALE));
+      atomicAdd(&sred[(half * 32 + tx) * 2 + 1], (unsigned long long)__float2ll_rn(s_sq * STAT_FIXED_SCALE));
+    }
+    __syncthreads();
+    if (tid < 2 * COUT) atomicAdd(stats + (size_t)b * COUT * 2 + tid, sred[tid]);
+  }
+}
+
+bool head_conv_fast_path(int c_in, int R, int Cout) {
+  return Cout == 64 && R % HEAD_TW == 0 && R % HEAD_TH == 0 &&
+         (size_t)(c_in * 9 * 64 + c_in * (HEAD_TH + 2) * (HEAD_TW + 2)) * sizeof(float) <= 48 * 1024;
+}
+
 void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
-                      const float* bias, int B, int R, int Cout, bf16* out, cudaStream_t s) {
+                      const float* bias, int B, int R, int Cout, bf16* out, long long* stats, cudaStream_t s) {
+  if (head_conv_fast_path(c_cond + c_x, R, Cout)) {
+    const int cin = c_cond + c_x;
+    const size_t smem = (size_t)(cin * 9 * 64 + cin * (HEAD_TH + 2) * (HEAD_TW + 2)) * sizeof(float);
+    if (stats) CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * 64 * 2 * sizeof(long long), s));
+    const unsigned blocks = (unsigned)(B * (R / HEAD_TH) * (R / HEAD_TW));
+    head_conv64_kernel<<<blocks, HEAD_TW * HEAD_TH, smem, s>>>(cond, x, c_cond, c_x, w_kc, bias, B, R, out,
+                                                              reinterpret_cast<unsigned long long*>(stats));
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  REQUIRE(stats == nullptr, "head conv: the generic path does not produce statistics");
   REQUIRE(Cout % 8 == 0 && Cout <= 2048, "head conv: Cout must be a multiple of 8");
   const int tpp = Cout / 8;
   const int threads = 256 / tpp * tpp > 0 ? (256 / tpp) * tpp : tpp;
@@ -352,11 +464,98 @@ __global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
   }
 }
 
+// Fast path (C/8 a power of two <= 32, i.e. C = 64): C/8 lanes share a pixel, each owning 8
+// channels, so a tap is one fully coalesced 16-byte load per lane; the OC partial dot products are
+// combined with xor-shuffles and lane o < OC of the group applies the posterior update of channel o.
+template <int OC>
+__global__ void __launch_bounds__(256) tail_split_kernel(TailPlan t) {
+  extern __shared__ float w_s[];   // [OC][9][C]
+  const int C = t.C, R = t.R;
+  for (int i = threadIdx.x; i < OC * 9 * C; i += blockDim.x) w_s[i] = t.w[i];
+  __syncthreads();
+  const int lpp = C >> 3;                       // lanes per pixel
+  const int sub = threadIdx.x & (lpp - 1);
+  const long long pix = (long long)blockIdx.x * (blockDim.x / lpp) + threadIdx.x / lpp;
+  const long long npix = (long long)t.B * R * R;
+  const bool live = pix < npix;                 // whole pixel groups are live or dead together
+  const int xw = live ? (int)(pix % R) : 0;
+  const int yh = live ? (int)((pix / R) % R) : 0;
+  const int b = live ? (int)(pix / ((long long)R * R)) : 0;
+  float acc[OC];
+#pragma unroll
+  for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+  if (live) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy < 0 || yy >= R || xx < 0 || xx >= R) continue;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(t.src + (((size_t)b * R + yy) * R + xx) * C + sub * 8)), f);
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {
+        const float4* wr = reinterpret_cast<const float4*>(w_s + (o * 9 + tap) * C + sub * 8);
+        const float4 w0 = wr[0], w1 = wr[1];
+        acc[o] = fmaf(f[0], w0.x, acc[o]); acc[o] = fmaf(f[1], w0.y, acc[o]);
+        acc[o] = fmaf(f[2], w0.z, acc[o]); acc[o] = fmaf(f[3], w0.w, acc[o]);
+        acc[o] = fmaf(f[4], w1.x, acc[o]); acc[o] = fmaf(f[5], w1.y, acc[o]);
+        acc[o] = fmaf(f[6], w1.z, acc[o]); acc[o] = fmaf(f[7], w1.w, acc[o]);
+      }
+    }
+  }
+  for (int m = 1; m < lpp; m <<= 1) {
+#pragma unroll
+    for (int o = 0; o < OC; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+  }
+  if (!live || sub >= OC) return;
+  float eps = 0.f;
+#pragma unroll
+  for (int o = 0; o < OC; ++o) if (o == sub) eps = acc[o] + t.bias[o];
+  const size_t plane = (size_t)R * R;
+  const size_t idx = ((size_t)b * OC + sub) * plane + (size_t)yh * R + xw;
+  if (t.eps_out) t.eps_out[idx] = eps;
+  if (t.x == nullptr) return;
+  const int ts = t.ctl->t, T = t.ctl->T;
+  const float a = t.coefs[ts], bc = t.coefs[T + ts], c1 = t.coefs[2 * T + ts], c2 = t.coefs[3 * T + ts];
+  const float sigma = expf(0.5f * t.coefs[4 * T + ts]);
+  float z = 0.f;
+  const int mode = t.ctl->noise_mode;
+  if (ts > 0) {
+    if (mode == 1 || mode == 3) {
+      const float* zp = t.ctl->noise;
+      if (zp) {
+        if (mode == 1) zp += (size_t)(T - ts) * (size_t)t.ctl->numel;
+        z = __ldg(zp + idx);
+      }
+    } else if (mode == 2) {
+      const unsigned long long seed = t.ctl->seed;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+      const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
+      z = zz[sub & 3];
+    }
+  }
+  t.x[idx] = posterior_update(t.x[idx], eps, z, a, bc, c1, c2, sigma);
+}
+
 void launch_tail(const TailPlan& t, cudaStream_t s) {
   REQUIRE(t.C % 8 == 0, "tail conv: C must be a multiple of 8");
   const long long npix = (long long)t.B * t.R * t.R;
   const size_t smem = (size_t)t.OC * 9 * t.C * sizeof(float);
   REQUIRE(smem <= 48 * 1024, "tail conv: weights exceed 48 KB of shared memory");
+  const int lpp = t.C / 8;
+  if (lpp >= 4 && lpp <= 32 && (lpp & (lpp - 1)) == 0) {
+    const int ppb = 256 / lpp;
+    const unsigned blocks = (unsigned)((npix + ppb - 1) / ppb);
+    switch (t.OC) {
+      case 1: tail_split_kernel<1><<<blocks, 256, smem, s>>>(t); break;
+      case 3: tail_split_kernel<3><<<blocks, 256, smem, s>>>(t); break;
+      case 4: tail_split_kernel<4><<<blocks, 256, smem, s>>>(t); break;
+      default: throw Error("tail conv: out_channel must be 1, 3 or 4");
+    }
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   const unsigned blocks = (unsigned)((npix + 127) / 128);
   switch (t.OC) {
     case 1: tail_kernel<1><<<blocks, 128, smem, s>>>(t); break;

@@ -36,8 +36,10 @@ int chan_stats_chunks(int HW, int C);
 void launch_chan_stats(const ChanStatsPlan& g, cudaStream_t s);
 
 // ---- head conv (unet.py:196-197, downs.0): fp32 NCHW cond/x -> 3x3 conv -> NHWC bf16
+// `stats` (optional, fast path only): [B][Cout][2] int64 fixed-point sums of the output, zeroed here.
+bool head_conv_fast_path(int c_in, int R, int Cout);
 void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
-                      const float* bias, int B, int R, int Cout, bf16* out, cudaStream_t s);
+                      const float* bias, int B, int R, int Cout, bf16* out, long long* stats, cudaStream_t s);
 
 // ---- tail (unet.py:233 final conv on the normalised tensor) fused with the posterior update
 // (diffusion.py:144-187): eps = conv3x3(src) ; x0 = clamp(A x - B eps) ; x' = c1 x0 + c2 x + sigma z

@@ -1,0 +1,91 @@
+// Microbenchmark: issue rate of tcgen05.mma.cta_group::1.kind::f16 (M=128, K=16) as a function of N,
+// operands in shared memory (SWIZZLE_128B K-major, contents irrelevant). One CTA per SM.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu && ./umma_rate
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+  uint64_t d = 0;
+  d |= (uint64_t)((a & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int M, int iters, int stages, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tslot;
+  if (threadIdx.x == 0) {
+    const uint32_t id = idesc(M, N);
+    const uint32_t stage_bytes = 16384 + N * 128;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int st = i % stages;
+      const uint32_t sa = base + st * stage_bytes, sb = sa + 16384;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = desc_sw128(sa + k * 32), db = desc_sw128(sb + k * 32);
+        const uint32_t accum = (i | k) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (uint32_t)((i & 1) * N)),
+                     "l"(da), "l"(db), "r"(id), "r"(accum)
+                     : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    const long long t2 = clock64();
+    out[blockIdx.x * 2] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 148 * 2 * sizeof(long long));
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 2000;
+  for (int grid : {1, 148})
+    for (int M : {128, 64})
+      for (int N : {64, 128, 256}) {
+        const int stages = (190 * 1024) / (16384 + N * 128);
+        rate_kernel<<<grid, 128, 200 * 1024>>>(N, M, iters, stages, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        long long h[2];
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("grid %3d M %3d N %3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (%.0f MAC/cyc/SM)\n", grid, M, N,
+               (double)h[0] / (iters * 4), (double)h[1] / (iters * 4), (double)M * N * 16 / ((double)h[1] / (iters * 4)));
+      }
+  return 0;
+}
