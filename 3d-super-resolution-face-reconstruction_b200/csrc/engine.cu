@@ -39,6 +39,19 @@ static void pack_slice(const float* src, bf16* dst, int Cout, int cseg, int c0, 
   CUDA_CHECK(cudaGetLastError());
 }
 
+// Identity block appended along K: out += 1.0 * x, i.e. the ResnetBlock's identity shortcut
+// (unet.py:110 with res_conv = nn.Identity) rides the GEMM as one more 1x1 segment instead of being
+// fetched by the epilogue threads. bf16 x * 1.0 is exact in the fp32 accumulator.
+__global__ void pack_identity_kernel(bf16* __restrict__ dst, int Cout, int cpad, int k_off, int k_total) {
+  const long long total = (long long)Cout * cpad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cpad);
+    const int o = (int)(idx / cpad);
+    dst[(size_t)o * k_total + k_off + c] = __float2bfloat16_rn(c == o ? 1.f : 0.f);
+  }
+}
+
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 Workspace::~Workspace() {
@@ -245,7 +258,14 @@ void Engine::finalize_weights(cudaStream_t s) {
     pc.k_total = taps * cpad + r0pad + r1pad;
     pc.w = (bf16*)dalloc((size_t)cout * pc.k_total * sizeof(bf16));
     pack_slice(T_(wkey + ".weight"), pc.w, cout, cin, 0, cin, taps, cpad, 0, pc.k_total, s);
-    if (c_res0) pack_slice(T_(reskey + ".weight"), pc.w, cout, c_res0, 0, c_res0 + c_res1, 1, r0pad, taps * cpad, pc.k_total, s);
+    if (c_res0 && reskey == "identity") {
+      REQUIRE(c_res0 == cout && c_res1 == 0, "internal: identity shortcut needs Cin == Cout");
+      const long long total = (long long)cout * r0pad;
+      pack_identity_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, s>>>(pc.w, cout, r0pad,
+                                                                                             taps * cpad, pc.k_total);
+      CUDA_CHECK(cudaGetLastError());
+    } else if (c_res0)
+      pack_slice(T_(reskey + ".weight"), pc.w, cout, c_res0, 0, c_res0 + c_res1, 1, r0pad, taps * cpad, pc.k_total, s);
     if (c_res1) pack_slice(T_(reskey + ".weight"), pc.w, cout, c_res1, c_res0, c_res0 + c_res1, 1, r1pad, taps * cpad + r0pad, pc.k_total, s);
     convs_[name] = pc;
     return &convs_[name];
@@ -290,14 +310,14 @@ void Engine::finalize_weights(cudaStream_t s) {
                                    (size_t)l.cout * inner * sizeof(float), cudaMemcpyDeviceToDevice, s));
         add_vec(T_(rb + ".noise_func.noise_func.0.bias"), T_(rb + ".block1.block.3.bias"), ball_ + off, l.cout, s);
         const bool has_res = cin != l.cout;
-        PackedConv* c2 = pack(l.name + ".c2", rb + ".block2.block.3", l.cout, l.cout, 9, rb + ".res_conv",
-                              has_res ? l.c_x : 0, has_res ? l.c_skip : 0);
+        if (!has_res) REQUIRE(l.c_skip == 0, "identity residual over a concatenated input is not supported");
+        PackedConv* c2 = pack(l.name + ".c2", rb + ".block2.block.3", l.cout, l.cout, 9,
+                              has_res ? rb + ".res_conv" : std::string("identity"), l.c_x, has_res ? l.c_skip : 0);
         c2->bias = (float*)dalloc((size_t)l.cout * sizeof(float));
         add_vec(T_(rb + ".block2.block.3.bias"), has_res ? T_(rb + ".res_conv.bias") : nullptr, c2->bias, l.cout, s);
-        if (!has_res) REQUIRE(l.c_skip == 0, "identity residual over a concatenated input is not supported");
         if (l.attn) {
           pack(l.name + ".qkv", l.name + ".attn.qkv", 3 * l.cout, l.cout, 1, "", 0, 0);
-          PackedConv* o = pack(l.name + ".out", l.name + ".attn.out", l.cout, l.cout, 1, "", 0, 0);
+          PackedConv* o = pack(l.name + ".out", l.name + ".attn.out", l.cout, l.cout, 1, "identity", l.cout, 0);
           o->bias = T_(l.name + ".attn.out.bias");
         }
         break;
@@ -507,9 +527,9 @@ void Engine::build_workspace(Workspace& ws) {
                      noise_total_, nullptr, xin.H, xin.W, true);
         Act hn = group_norm(l.name + ".block2", h, nullptr, rb + ".block2.block.0", true);
         const PackedConv& c2 = convs_.at(l.name + ".c2");
-        const bool has_res = c2.c_res0 > 0;
-        cur = conv(l.name + ".conv2", hn, 9, 1, false, c2, has_res ? &xin : nullptr,
-                   (has_res && is_up) ? &skip : nullptr, c2.bias, 0, has_res ? nullptr : xin.ptr, xin.H, xin.W, true);
+        // the shortcut (res_conv 1x1, or identity) is one or two extra 1x1 K segments of this GEMM
+        cur = conv(l.name + ".conv2", hn, 9, 1, false, c2, &xin, is_up ? &skip : nullptr, c2.bias, 0, nullptr, xin.H,
+                   xin.W, true);
         if (l.attn) {
           const Act ain = cur;
           Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);
@@ -520,7 +540,7 @@ void Engine::build_workspace(Workspace& ws) {
             launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
           }});
           const PackedConv& po = convs_.at(l.name + ".out");
-          cur = conv(l.name + ".attn.out", ao, 1, 1, false, po, nullptr, nullptr, po.bias, 0, ain.ptr, ain.H, ain.W,
+          cur = conv(l.name + ".attn.out", ao, 1, 1, false, po, &ain, nullptr, po.bias, 0, nullptr, ain.H, ain.W,
                      true);
         }
         if (l.name.compare(0, 6, "downs.") == 0) feats.push_back(cur);
