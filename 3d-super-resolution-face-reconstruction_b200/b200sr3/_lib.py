@@ -45,6 +45,9 @@ _SIGNATURES = {
                                        C.POINTER(C.c_double), C.c_char_p, C.c_int, C.POINTER(C.c_int), _P]),
     "b200sr3_conv2d": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float), _P]),
+    "b200sr3_conv_block": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int,
+                                     _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                     C.POINTER(C.c_float), _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -257,4 +257,158 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
   });
 }
 
+
+int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int C1, const float* gamma,
+                       const float* beta, int groups, int swish, const float* w, const float* bias, const float* r0,
+                       int Cr0, const float* r1, int Cr1, const float* wres, int B, int H, int W, int Cout,
+                       int upsample2x, float* y, float* stats_out, int iters, float* avg_ms, void* stream) {
+  return guarded([&] {
+    REQUIRE(x0 && w && y, "conv_block: null pointer");
+    REQUIRE((x1 != nullptr) == (C1 > 0) && (r0 != nullptr) == (Cr0 > 0) && (r1 != nullptr) == (Cr1 > 0),
+            "conv_block: pointer / channel count mismatch");
+    REQUIRE((Cr0 + Cr1 > 0) == (wres != nullptr), "conv_block: shortcut weights / sources mismatch");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(std::string("no CUDA device available (") + cudaGetErrorString(e) + "): no CPU fallback");
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major == 10, "conv_block: device is not sm_100");
+    CUDA_CHECK(cudaSetDevice(device));
+    conv_init_device();
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) {
+      void* p = nullptr;
+      CUDA_CHECK(cudaMalloc(&p, bytes));
+      tmp.push_back(p);
+      return p;
+    };
+    struct Cleanup {
+      std::vector<void*>& v;
+      ~Cleanup() { for (void* p : v) cudaFree(p); }
+    } cleanup{tmp};
+    const bool up = upsample2x != 0;
+    REQUIRE(conv_halo_eligible(H, W, (C0 % 64 == 0) && (C1 % 64 == 0) && (Cr0 % 64 == 0) && (Cr1 % 64 == 0), Cout),
+            "conv_block: shape not supported by the halo conv (H % 16, W % 8, W >= 16, channels % 64)");
+    REQUIRE(!up || (Cr0 + Cr1 == 0), "conv_block: a folded upsample has no shortcut");
+
+    auto make_act = [&](const float* src, int C, bool want_stats) {
+      Act a;
+      a.B = B; a.H = H; a.W = W; a.C = C;
+      a.ptr = (bf16*)dalloc(a.elems() * sizeof(bf16));
+      launch_nchw_to_nhwc(src, a.ptr, B, C, H, W, s);
+      if (want_stats) {
+        a.stat_slots = 1;
+        a.stats = (long long*)dalloc((size_t)B * C * 2 * sizeof(long long));
+        ChanStatsPlan g;
+        g.src = a.ptr; g.B = B; g.HW = H * W; g.C = C; g.chunks = 1; g.chansum = a.stats;
+        launch_chan_stats(g, s);
+      }
+      return a;
+    };
+    const bool has_gn = gamma != nullptr;
+    REQUIRE(!has_gn || beta != nullptr, "conv_block: GroupNorm needs gamma and beta");
+    std::vector<HaloSource> srcs;
+    Act a0 = make_act(x0, C0, has_gn);
+    srcs.push_back(HaloSource{a0, 9, has_gn ? 0 : -1});
+    Act a1;
+    if (C1) { a1 = make_act(x1, C1, has_gn); srcs.push_back(HaloSource{a1, 9, has_gn ? C0 : -1}); }
+    if (Cr0) srcs.push_back(HaloSource{make_act(r0, Cr0, false), 1, -1});
+    if (Cr1) srcs.push_back(HaloSource{make_act(r1, Cr1, false), 1, -1});
+    float2* gn = nullptr;
+    if (has_gn) {
+      gn = (float2*)dalloc((size_t)B * (C0 + C1) * sizeof(float2));
+      GnPlan g;
+      g.C0 = C0; g.C1 = C1; g.B = B; g.HW = H * W; g.groups = groups;
+      g.stats0 = a0.stats; g.slots0 = 1; g.stats1 = C1 ? a1.stats : nullptr; g.slots1 = 1;
+      float* dg = (float*)dalloc((size_t)(C0 + C1) * sizeof(float));
+      float* db = (float*)dalloc((size_t)(C0 + C1) * sizeof(float));
+      CUDA_CHECK(cudaMemcpyAsync(dg, gamma, (size_t)(C0 + C1) * sizeof(float), cudaMemcpyDefault, s));
+      CUDA_CHECK(cudaMemcpyAsync(db, beta, (size_t)(C0 + C1) * sizeof(float), cudaMemcpyDefault, s));
+      g.gamma = dg; g.beta = db;
+      launch_gn_scale_shift(g, gn, s);
+    }
+    Act out;
+    out.B = B; out.C = Cout; out.H = up ? 2 * H : H; out.W = up ? 2 * W : W;
+    out.ptr = (bf16*)dalloc(out.elems() * sizeof(bf16));
+    PackedConv pc;
+    const int cin = C0 + C1;
+    pc.cout = Cout; pc.taps = 9; pc.cin_main = cin; pc.c_res0 = Cr0; pc.c_res1 = Cr1;
+    if (up) {
+      pc.up_folded = true;
+      pc.k_total = 4 * cin;
+      pc.w = (bf16*)dalloc((size_t)4 * Cout * pc.k_total * sizeof(bf16));
+      launch_pack_upfold_weight(w, pc.w, Cout, cin, cin, s);
+    } else {
+      pc.k_total = 9 * cin + Cr0 + Cr1;
+      pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
+      launch_pack_conv_weight(w, pc.w, Cout, cin, 9, cin, 0, pc.k_total, s);
+      if (Cr0 + Cr1) launch_pack_conv_weight(wres, pc.w, Cout, Cr0 + Cr1, 1, Cr0 + Cr1, 9 * cin, pc.k_total, s);
+    }
+    ConvStats st;
+    if (stats_out) {
+      st.slots = conv_halo_stat_slots(out, up);
+      st.partial = (long long*)dalloc((size_t)B * st.slots * Cout * 2 * sizeof(long long));
+    }
+    const char* tev = getenv("B200SR3_CONV_TIMING");
+    const bool timing = tev && tev[0] == '1';
+    if (timing) {
+      st.dbg = (unsigned long long*)dalloc(256 * 16 * sizeof(unsigned long long));
+      CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 16 * sizeof(unsigned long long)));
+    }
+    Op op = make_conv_halo_op("conv_block", srcs, up, pc, bias, 0, nullptr, out, gn, cin, swish != 0,
+                              (stats_out || timing) ? &st : nullptr);
+    op.run(s);
+    launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (stats_out) {
+      std::vector<long long> h((size_t)B * st.slots * Cout * 2);
+      CUDA_CHECK(cudaMemcpy(h.data(), st.partial, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      std::vector<float> f((size_t)B * Cout * 2);
+      for (int b = 0; b < B; ++b)
+        for (int c = 0; c < Cout * 2; ++c) {
+          long long a = 0;
+          for (int k = 0; k < st.slots; ++k) a += h[((size_t)b * st.slots + k) * Cout * 2 + c];
+          f[(size_t)b * Cout * 2 + c] = (float)((double)a * STAT_FIXED_INV);
+        }
+      CUDA_CHECK(cudaMemcpy(stats_out, f.data(), f.size() * sizeof(float), cudaMemcpyDefault));
+    }
+    if (iters > 0 && avg_ms) {
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, s));
+      for (int i = 0; i < iters; ++i) op.run(s);
+      CUDA_CHECK(cudaEventRecord(e1, s));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      *avg_ms = ms / iters;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+    if (timing) {
+      std::vector<unsigned long long> h(256 * 16);
+      CUDA_CHECK(cudaMemcpy(h.data(), st.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      double acc[16] = {0};
+      int n = 0;
+      for (int c = 0; c < 256; ++c) {
+        if (h[c * 16 + 2] == 0) continue;
+        ++n;
+        for (int k = 0; k < 16; ++k) acc[k] += (double)h[c * 16 + k];
+      }
+      if (n) {
+        const double sup = acc[2] / n;
+        auto per = [&](int k) { return acc[k] / n / sup; };
+        fprintf(stderr,
+                "halo timing (avg over %d CTAs, %.1f super tiles each; cycles per super tile): total %.0f | A producer "
+                "waits empty %.0f | MMA waits A %.0f, W %.0f, TMEM %.0f | epilogue waits accum %.0f | transform waits "
+                "A full %.0f, works %.0f\n",
+                n, sup, per(1), per(0), per(4), per(5), per(6), per(8), per(10), per(11));
+      }
+    }
+  });
+}
+
 }  // extern "C"

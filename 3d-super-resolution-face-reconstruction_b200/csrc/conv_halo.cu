@@ -1,0 +1,208 @@
+// Host side of the halo-resident convolution (conv_halo.cuh): tensor maps, segment list, tile-shape
+// choice, launch closure.
+#include <memory>
+#include <mutex>
+
+#include "engine.cuh"
+
+namespace b200sr3 {
+
+CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2);   // conv_umma.cu
+
+static int g_halo_sms = 148;
+
+template <int BN, int MT, bool GN>
+static void set_attr() {
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<BN, MT>::TOTAL));
+}
+
+void conv_halo_init_device() {
+  set_attr<64, 1, false>();  set_attr<64, 1, true>();
+  set_attr<64, 2, false>();  set_attr<64, 2, true>();
+  set_attr<128, 1, false>(); set_attr<128, 1, true>();
+  set_attr<128, 2, false>(); set_attr<128, 2, true>();
+  set_attr<256, 1, false>(); set_attr<256, 1, true>();
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
+}
+
+template <int BN, int MT>
+static void launch_halo(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
+  if (gn) conv_halo_kernel<BN, MT, true><<<grid, HALO_THREADS, HaloSmem<BN, MT>::TOTAL, s>>>(p);
+  else conv_halo_kernel<BN, MT, false><<<grid, HALO_THREADS, HaloSmem<BN, MT>::TOTAL, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout) {
+  return c_multiple_of_64_all && (cout % 64 == 0) && (H % HALO_TH == 0) && (W % HALO_TW == 0) && W >= 16 && H >= 16;
+}
+
+// CTAs a (n tile, image) segment of seg_len_super super tiles can be spread over when total_super
+// super tiles are split into contiguous runs over `grid` CTAs (same owner formula as the kernel).
+static int slots_needed(long long seg_len_super, long long total_super, long long grid) {
+  int need = 1;
+  for (long long seg = 0; seg * seg_len_super < total_super; ++seg) {
+    const int first_cta = (int)(((seg * seg_len_super + 1) * grid - 1) / total_super);
+    const int last_cta = (int)((((seg + 1) * seg_len_super) * grid - 1) / total_super);
+    need = std::max(need, last_cta - first_cta + 1);
+  }
+  return need;
+}
+
+int conv_halo_stat_slots(const Act& out, bool upsample2x) {
+  const int PH = upsample2x ? out.H / 2 : out.H, PW = upsample2x ? out.W / 2 : out.W;
+  const long long seg_len = (long long)(PH / HALO_TH) * (PW / HALO_TW) * (upsample2x ? 4 : 1);
+  int need = 1;
+  for (int mt = 1; mt <= 2; ++mt) {
+    if (seg_len % mt) continue;
+    for (int tn = 1; tn <= 16; tn *= 2) {
+      const long long total = seg_len / mt * out.B * tn;
+      need = std::max(need, slots_needed(seg_len / mt, total, std::min<long long>(total, g_halo_sms)));
+    }
+  }
+  return need;
+}
+
+Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
+                     const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
+                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats) {
+  REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
+  const Act& a0 = srcs[0].act;
+  const int PH = a0.H, PW = a0.W;
+  auto pp = std::make_shared<ConvHaloParams>();
+  ConvHaloParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  p.num_par = upsample2x ? 4 : 1;
+  REQUIRE(out.B == a0.B && out.H == (upsample2x ? 2 : 1) * PH && out.W == (upsample2x ? 2 : 1) * PW,
+          "halo conv: output shape mismatch");
+  REQUIRE(PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16, "halo conv: unsupported spatial size");
+  REQUIRE(out.C == w.cout && out.C % 64 == 0, "halo conv: Cout must be a multiple of 64");
+
+  // ---- segments; K order of the packed weights: [tap][all main channels] then the 1x1 shortcut blocks
+  int c_main = 0;
+  for (const HaloSource& s : srcs)
+    if (s.ntaps != 1) c_main += s.act.C;
+  REQUIRE(c_main == w.cin_main && c_main % CONV_BLOCK_K == 0, "halo conv: main channel count mismatch");
+  const int main_taps = upsample2x ? 4 : 9;
+  int c_seen = 0, k_short = main_taps * c_main, kblocks = 0;
+  bool any_gn = false;
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    const HaloSource& s = srcs[i];
+    const Act& a = s.act;
+    REQUIRE(a.B == out.B && a.H == PH && a.W == PW && a.C % CONV_BLOCK_K == 0, "halo conv: source shape mismatch");
+    REQUIRE(s.ntaps == 9 || s.ntaps == 1, "halo conv: a source is 3x3 or 1x1");
+    REQUIRE(!(upsample2x && s.ntaps == 1), "halo conv: a folded upsample has no shortcut");
+    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_tiled(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.ptr, dims, strides, box, estr,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(halo) failed with CUresult " + std::to_string((int)r));
+    HaloSeg& sg = p.seg[i];
+    sg.map = (int)i;
+    sg.cblocks = a.C / CONV_BLOCK_K;
+    sg.gn_off = s.gn_off;
+    if (s.ntaps != 1) {
+      REQUIRE(k_short == main_taps * c_main && kblocks == (c_seen / CONV_BLOCK_K) * main_taps,
+              "halo conv: main sources must come first");
+      sg.ntaps = main_taps;
+      sg.k_base = c_seen;
+      sg.k_tap_stride = c_main;
+      c_seen += a.C;
+    } else {
+      sg.ntaps = 1;
+      sg.k_base = k_short;
+      sg.k_tap_stride = 0;
+      k_short += a.C;
+    }
+    kblocks += sg.ntaps * sg.cblocks;
+    any_gn |= s.gn_off >= 0;
+    if (s.gn_off >= 0) REQUIRE(gn != nullptr && s.gn_off + a.C <= gn_C, "halo conv: GroupNorm table too small");
+  }
+  p.num_segs = (int)srcs.size();
+  REQUIRE(k_short == w.k_total, "halo conv: packed weight K does not match the segment list");
+  REQUIRE(w.up_folded == upsample2x, "halo conv: weight packing / upsample mismatch");
+  p.tiles_w = PW / HALO_TW;
+  p.tiles_h = PH / HALO_TH;
+  p.B = out.B; p.H = PH; p.W = PW; p.Cout = out.C;
+  p.out_H = out.H; p.out_W = out.W;
+  p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
+  p.out = out.ptr;
+  p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
+
+  // ---- (BLOCK_N, MT): lowest modelled time. Per 64-channel block a super tile costs
+  // max(MMA cycles, L2->SM bytes / rate); a CTA runs ceil(super tiles / SMs) of them.
+  const long long tiles_img = (long long)p.tiles_w * p.tiles_h;
+  const long long m_tiles = tiles_img * p.num_par * out.B;
+  int bn = 0, mt = 0;
+  {
+    int fbn = 0, fmt = 0;
+    if (const char* e = getenv("B200SR3_HALO_BN")) fbn = atoi(e);
+    if (const char* e = getenv("B200SR3_HALO_MT")) fmt = atoi(e);
+    double best = 1e30;
+    const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};
+    for (auto& c : cand) {
+      if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
+      if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
+      const double mma_cyc = c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : 48.0);   // per MMA, measured
+      double per_super = 0.0;
+      for (int i = 0; i < p.num_segs; ++i) {
+        const double mma = p.seg[i].ntaps * c[1] * 4 * mma_cyc;
+        const double bytes = c[1] * (double)HALO_BYTES + p.seg[i].ntaps * c[0] * 128.0;
+        per_super += p.seg[i].cblocks * std::max(mma, bytes / 56.0);
+      }
+      per_super += 300.0 + c[1] * c[0] * 5.0;                                      // epilogue drain, not overlapped at the end
+      const long long supers = m_tiles / c[1] * (out.C / c[0]);
+      const double rounds = (double)((supers + g_halo_sms - 1) / g_halo_sms);
+      const double cost = rounds * per_super;
+      if (cost < best) { best = cost; bn = c[0]; mt = c[1]; }
+    }
+    REQUIRE(bn != 0, "halo conv: no tile shape fits (check B200SR3_HALO_BN / B200SR3_HALO_MT)");
+  }
+  p.tiles_n = out.C / bn;
+  p.total_super = (int)(m_tiles / mt * p.tiles_n);
+  p.seg_len_super = (int)(tiles_img * p.num_par / mt);
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)w.k_total, (cuuint64_t)w.cout * p.num_par};
+    cuuint64_t strides[1] = {(cuuint64_t)w.k_total * 2};
+    cuuint32_t box[2] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, estr,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
+  }
+  const int grid = std::min(p.total_super, g_halo_sms);
+  if (const char* ab = getenv("B200SR3_CONV_ABLATE")) p.ablate = atoi(ab);
+  if (stats) p.dbg = stats->dbg;
+  if (stats && stats->partial) {
+    REQUIRE(slots_needed(p.seg_len_super, p.total_super, grid) <= stats->slots,
+            "halo conv: statistics scratch has too few slots");
+    p.stat_partial = stats->partial;
+    p.stat_slots = stats->slots;
+  }
+
+  Op op;
+  op.name = name;
+  op.is_conv = true;
+  {
+    const double m = (double)out.B * out.H * out.W;
+    double k = 0;
+    for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
+    op.flops = 2.0 * m * (double)out.C * k;
+  }
+  op.run = [pp, grid, bn, mt, any_gn](cudaStream_t s) {
+    if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
+    else if (bn == 128 && mt == 2) launch_halo<128, 2>(*pp, any_gn, grid, s);
+    else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);
+    else if (mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);
+    else launch_halo<64, 1>(*pp, any_gn, grid, s);
+  };
+  return op;
+}
+
+}  // namespace b200sr3

@@ -1,0 +1,500 @@
+// Halo-resident implicit-GEMM 3x3 convolution (tcgen05 / TMEM / TMA), second generation.
+//
+// conv_umma.cuh fetches one 16 KB A tile per filter tap, i.e. it pulls the input through L2 nine
+// times; measured on B200 that L2->SM traffic, not the tensor pipe, bounds every conv with
+// Cout <= 256 (profiles/r01b). Here ONE 4-D TMA box load brings the (8+2) x (16+2) pixel x
+// 64-channel HALO of an 8x16-pixel output tile into shared memory (128 B per pixel, 128B-swizzled)
+// and the nine taps are nine tcgen05 A descriptors into that same tile: tap (ky,kx) starts at
+// pixel ky*10+kx - a 128-byte row that is not 1024-byte aligned - with SBO = 10 pixels (1280 B)
+// between the 8-row groups (a group = 8 consecutive x of one output row). The hardware swizzles on
+// absolute shared-memory address bits, so this reads exactly the shifted window
+// (tools/micro/halo_umma.cu proves it bit-exactly and shows the MMA rate is unchanged).
+// A traffic drops from 9 x 16 KB to 22.5 KB per 64-channel block.
+//
+// Because the input now sits in shared memory ONCE per use, GroupNorm-apply + Swish
+// (unet.py:84-86, Block = GN -> Swish -> Conv) is fused in: four "transform" warps rewrite the
+// halo tile in place, y = swish(x * scale[b][c] + shift[b][c]) for in-image pixels (the conv's zero
+// padding must stay zero, so out-of-image pixels are left as TMA zero-filled them), between the
+// TMA arrival and the MMAs. The normalised tensor is never written to HBM; the channel concat
+// cat((x, skip), 1) (unet.py:261) is two K segments with their own tensor maps.
+//
+// K loop: segments (main source(s) with 9 taps [or the 4 parity taps of a folded nearest-2x
+// upsample], then raw 1x1 shortcut sources, unet.py:103-110) x 64-channel blocks x taps. Weights
+// stream through their own ring, one [BLOCK_N x 64] tile per (tap, block). A CTA processes MT
+// horizontally adjacent tiles against each weight tile (MT x fewer weight bytes from L2).
+//
+// Warp roles (384 threads): 0-3 = GroupNorm/Swish transform, 4-7 = epilogue (TMEM -> +bias[t] -> bf16
+// NHWC stores, GroupNorm statistics of the output), 8 = halo TMA producer, 9 = weight TMA producer,
+// 10 = TMEM allocator, 11 = MMA issuer. The single-thread roles carry the HIGHEST warp ids on purpose:
+// a scheduler (warp id % 4) prefers its highest-numbered ready warp, and with the issuer below the
+// ALU-heavy transform / epilogue warps the tensor pipe starved whenever those were busy.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace b200sr3 {
+
+constexpr int HALO_W = 10, HALO_H = 18;                  // (8+2) x (16+2) pixels
+constexpr int HALO_TW = 8, HALO_TH = 16;                 // output tile
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;        // 23040: what one TMA box load delivers
+constexpr int HALO_STRIDE = 23552;                       // rounded up to the 1024 B swizzle period
+constexpr int HALO_THREADS = 384;
+constexpr int HALO_A_STAGES = 3;
+constexpr int HALO_MAX_SEGS = 4;
+
+struct HaloSeg {
+  int map;           // a_map index
+  int cblocks;       // 64-channel blocks of this source
+  int ntaps;         // 9: 3x3; 4: parity 2x2 of a folded upsample; 1: 1x1 shortcut (centre pixel)
+  int k_base;        // K column of (tap 0, block 0) in the packed weights
+  int k_tap_stride;  // K columns between consecutive taps
+  int gn_off;        // channel offset of this source in the GN table; < 0: raw input, no transform
+};
+
+struct alignas(64) ConvHaloParams {
+  CUtensorMap a_map[HALO_MAX_SEGS];
+  CUtensorMap w_map;
+  HaloSeg seg[HALO_MAX_SEGS];
+  int num_segs;
+  int num_par;                     // 1, or 4 (folded nearest-2x upsample: output parity (y&1, x&1))
+  int tiles_w, tiles_h;            // 8x16 tiles per image over the pixel space the tiles walk
+  int B, H, W, Cout;               // pixel space the tiles walk (the SOURCE grid when num_par == 4)
+  int out_H, out_W;
+  int tiles_n, total_super;        // N tiles; super tiles (MT tiles each) in the launch
+  int seg_len_super;               // super tiles per (n tile, image) = tiles_w*tiles_h*num_par/MT
+  const float* bias;               // [Cout] or a [rows][stride] table indexed by ctl->t
+  int bias_t_stride;
+  const StepCtl* ctl;
+  bf16* out;                       // NHWC [B][out_H][out_W][Cout]
+  const float2* gn;                // [B][gn_C] (scale, shift) of the fused GroupNorm (null: none)
+  int gn_C;
+  int gn_swish;
+  long long* stat_partial;         // as ConvParams::stat_partial
+  int stat_slots;
+  // measurement only (B200SR3_CONV_ABLATE bit mask; results are then wrong): 1 = no global stores,
+  // 2 = transform arrives without touching the tile, 16 = no TMEM loads, 32 = no statistics math
+  int ablate;
+  // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv_block): [grid][16] cycle counters
+  unsigned long long* dbg;
+};
+
+#ifdef __CUDACC__
+template <int BLOCK_N, int MT>
+struct HaloSmem {
+  static constexpr int A_STAGE = MT * HALO_STRIDE;
+  static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
+  static constexpr int W_STAGE = BLOCK_N * 128;
+  static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 8;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
+  static constexpr int W_FIT = (BUDGET - A_BYTES - STAT_BYTES) / W_STAGE;
+  static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
+  static constexpr int W_OFFSET = A_BYTES;
+  static constexpr int STAT_OFFSET = W_OFFSET + W_STAGES * W_STAGE;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+  static_assert(W_STAGES >= 3, "weight ring too shallow");
+};
+
+// MUFU.TANH: max relative error 2^-11, far below the bf16 rounding of the value it produces
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// A descriptor into a halo tile: 8-row groups 10 pixels (1280 B) apart
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((HALO_W * 128) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+#define HDBG_DECL() unsigned long long hd[4] = {0ull, 0ull, 0ull, 0ull}; long long hd_t0 = 0
+#define HDBG_T0() do { if (p.dbg) hd_t0 = clock64(); } while (0)
+#define HDBG_ACC(i) do { if (p.dbg) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
+#define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
+
+template <int BLOCK_N, int MT, bool FUSE_GN>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+  using S = HaloSmem<BLOCK_N, MT>;
+  constexpr int AST = HALO_A_STAGES, WST = S::W_STAGES;
+  constexpr int NBUF = 2;
+  static_assert(NBUF * MT * BLOCK_N <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  long long* sstat = reinterpret_cast<long long*>(smem_gen + S::STAT_OFFSET);
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  // barriers: a_full[AST], a_ready[AST], a_empty[AST], w_full[WST], w_empty[WST], tmem_full[2], tmem_empty[2]
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_ready = [&](int s) { return bar_base + 8u * (AST + s); };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 * AST + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (3 * AST + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (3 * AST + WST + s); };
+  auto tmem_full = [&](int b) { return bar_base + 8u * (3 * AST + 2 * WST + b); };
+  auto tmem_empty = [&](int b) { return bar_base + 8u * (3 * AST + 2 * WST + NBUF + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * AST + 2 * WST + 2 * NBUF);
+  static_assert(8 * (3 * AST + 2 * 12 + 2 * NBUF) + 4 <= 512, "barrier area");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 8 && lane == 0) {
+    ptx::prefetch_tmap(&p.w_map);
+    for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < AST; ++s) {
+      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_ready(s), 128);
+      ptx::mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < WST; ++s) {
+      ptx::mbar_init(w_full(s), 1);
+      ptx::mbar_init(w_empty(s), 1);
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      ptx::mbar_init(tmem_full(b), 1);
+      ptx::mbar_init(tmem_empty(b), 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 10) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // contiguous run of super tiles; order: x tile fastest, y tile, parity, image, n tile
+  const int sup_begin = (int)(((long long)blockIdx.x * p.total_super) / gridDim.x);
+  const int sup_end = (int)(((long long)(blockIdx.x + 1) * p.total_super) / gridDim.x);
+  struct Tile { int n_tile, x0, y0, b, par; };
+  auto decode = [&](int sup, int mt) {
+    int tile = sup * MT + mt;
+    Tile t;
+    t.x0 = (tile % p.tiles_w) * HALO_TW; tile /= p.tiles_w;
+    t.y0 = (tile % p.tiles_h) * HALO_TH; tile /= p.tiles_h;
+    t.par = tile % p.num_par; tile /= p.num_par;
+    t.b = tile % p.B;
+    t.n_tile = tile / p.B;
+    return t;
+  };
+
+  if (warp == 8) {
+    if (ptx::elect_one()) {
+      // ---------------------------------------------------------------- halo producer
+      int as = 0; uint32_t aphase = 0;
+      HDBG_DECL();
+      const long long hd_start = p.dbg ? clock64() : 0;
+      for (int sup = sup_begin; sup < sup_end; ++sup) {
+        Tile t[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
+        for (int sg = 0; sg < p.num_segs; ++sg) {
+          const HaloSeg seg = p.seg[sg];
+          for (int cb = 0; cb < seg.cblocks; ++cb) {
+            HDBG_T0();
+            ptx::mbar_wait(a_empty(as), aphase ^ 1u);
+            HDBG_ACC(0);
+            ptx::mbar_expect_tx(a_full(as), MT * HALO_BYTES);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * HALO_STRIDE, &p.a_map[seg.map], a_full(as),
+                               cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
+            if (++as == AST) { as = 0; aphase ^= 1u; }
+          }
+        }
+      }
+      if (p.dbg) { hd[1] = (unsigned long long)(clock64() - hd_start); hd[2] = (unsigned long long)(sup_end - sup_begin); }
+      HDBG_FLUSH(0, 3);      // [0] A producer waits a_empty, [1] total, [2] super tiles
+    }
+  } else if (warp == 9) {
+    if (ptx::elect_one()) {
+      // ---------------------------------------------------------------- weight producer
+      int ws = 0; uint32_t wphase = 0;
+      for (int sup = sup_begin; sup < sup_end; ++sup) {
+        const Tile t = decode(sup, 0);
+        const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N;
+        for (int sg = 0; sg < p.num_segs; ++sg) {
+          const HaloSeg seg = p.seg[sg];
+          for (int cb = 0; cb < seg.cblocks; ++cb) {
+            for (int tap = 0; tap < seg.ntaps; ++tap) {
+              ptx::mbar_wait(w_empty(ws), wphase ^ 1u);
+              ptx::mbar_expect_tx(w_full(ws), S::W_STAGE);
+              ptx::tma_load_2d(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws),
+                               seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
+              if (++ws == WST) { ws = 0; wphase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ MMA issuer
+    // One elected thread runs the whole loop. A single thread retires dependent scalar instructions at
+    // ~5 cycles each while an N=64 MMA occupies the tensor pipe for only 48 cycles, so the loop is kept
+    // minimal: descriptors are (constant high word, low word advanced by adds), the tap window walks
+    // the halo tile incrementally, and the NEXT weight stage's barrier is probed before this tap's
+    // MMAs are issued so that its latency overlaps them.
+    if (ptx::elect_one()) {
+      constexpr uint32_t A_HI = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M, BLOCK_N);
+      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t w_lo0 = (((smem_base + S::W_OFFSET) & 0x3FFFFu) >> 4) | 0x10000u;
+      auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+      int as = 0, ws = 0;
+      uint32_t aphase = 0, wphase = 0;
+      bool ready = false;
+      int it = 0;
+      HDBG_DECL();
+      for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        const int par = decode(sup, 0).par;
+        HDBG_T0();
+        ptx::mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);
+        HDBG_ACC(2);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * MT * BLOCK_N);
+        uint32_t accum = 0;
+        for (int sg = 0; sg < p.num_segs; ++sg) {
+          const int ntaps = p.seg[sg].ntaps, cblocks = p.seg[sg].cblocks;
+          const int ntx = ntaps == 9 ? 3 : (ntaps == 4 ? 2 : 1);
+          const uint32_t pix0 = ntaps == 9 ? 0u : (ntaps == 4 ? (uint32_t)((par >> 1) * HALO_W + (par & 1)) : (uint32_t)(HALO_W + 1));
+          for (int cb = 0; cb < cblocks; ++cb) {
+            HDBG_T0();
+            ptx::mbar_wait(FUSE_GN ? a_ready(as) : a_full(as), aphase);
+            HDBG_ACC(0);
+            uint32_t a_lo = a_lo0 + (uint32_t)as * (uint32_t)(S::A_STAGE >> 4) + pix0 * 8u;
+            int tx = 0;
+            for (int tap = 0; tap < ntaps; ++tap) {
+              if (!ready) {
+                HDBG_T0();
+                ptx::mbar_wait(w_full(ws), wphase);
+                HDBG_ACC(1);
+              }
+              ptx::tc_fence_after();
+              const uint32_t b_lo = w_lo0 + (uint32_t)ws * (uint32_t)(S::W_STAGE >> 4);
+              const uint32_t wcur = w_empty(ws);
+              if (++ws == WST) { ws = 0; wphase ^= 1u; }
+              ready = ptx::mbar_test_wait(w_full(ws), wphase);      // look one stage ahead
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (HALO_STRIDE >> 4) + 2 * k), A_HI),
+                                 desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
+              }
+              ptx::umma_commit(wcur);
+              accum = 1;
+              a_lo += 8u;
+              if (++tx == ntx) { tx = 0; a_lo += (uint32_t)(HALO_W - ntx) * 8u; }
+            }
+            ptx::umma_commit(a_empty(as));
+            if (++as == AST) { as = 0; aphase ^= 1u; }
+          }
+        }
+        ptx::umma_commit(tmem_full(buf));
+      }
+      HDBG_FLUSH(4, 3);      // [4] MMA waits A ready, [5] waits W full, [6] waits TMEM empty
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int tid_e = threadIdx.x - 128;
+    const int lx = row & 7, ly = row >> 3;
+    const bool do_stats = p.stat_partial != nullptr;
+    const float* bias = p.bias;
+    if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
+    const int osc = p.num_par == 4 ? 2 : 1;
+    long long* sacc = sstat + wq * (2 * BLOCK_N);
+    if (do_stats)
+      for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
+
+    int it = 0;
+    HDBG_DECL();
+    for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      HDBG_T0();
+      ptx::mbar_wait(tmem_full(buf), use & 1u);
+      HDBG_ACC(0);
+      ptx::tc_fence_after();
+      Tile t0 = decode(sup, 0);
+      const int n0 = t0.n_tile * BLOCK_N;
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const Tile t = decode(sup, m);
+        const int y = t.y0 + ly, x = t.x0 + lx;
+        const size_t pix = ((size_t)t.b * p.out_H + (size_t)(y * osc + (t.par >> 1))) * p.out_W +
+                           (size_t)(x * osc + (t.par & 1));
+        bf16* out_row = p.out + pix * p.Cout + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          if (!(p.ablate & 16)) {
+            ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(c0 + j);
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
+          }
+          if (!(p.ablate & 1)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
+          }
+          if (do_stats && !(p.ablate & 32)) {
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
+            const float s_sum = warp_transpose_sum(f, lane);
+            const float s_sq = warp_transpose_sum(q, lane);
+            sacc[c0 + lane] += __float2ll_rn(s_sum * STAT_FIXED_SCALE);
+            sacc[BLOCK_N + c0 + lane] += __float2ll_rn(s_sq * STAT_FIXED_SCALE);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty(buf));
+
+      if (do_stats) {
+        const int seg = sup / p.seg_len_super;
+        if (sup + 1 == sup_end || (sup + 1) / p.seg_len_super != seg) {
+          // the CTA's run over this (n tile, image) segment ends: publish its partial sums
+          const long long G = gridDim.x, T = p.total_super;
+          const int first_cta = (int)((((long long)seg * p.seg_len_super + 1) * G - 1) / T);
+          const int last_cta = (int)((((long long)(seg + 1) * p.seg_len_super) * G - 1) / T);
+          const int slot = (int)blockIdx.x - first_cta;
+          epi_bar_sync();
+          for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
+            const int col = item % BLOCK_N;
+            const int st = item / BLOCK_N;
+            long long a = 0;
+#pragma unroll
+            for (int ww = 0; ww < 4; ++ww) a += sstat[(ww * 2 + st) * BLOCK_N + col];
+            long long* dst = p.stat_partial + (((size_t)t0.b * p.stat_slots + slot) * p.Cout + (n0 + col)) * 2 + st;
+            *dst = a;
+            if ((int)blockIdx.x == last_cta)
+              for (int sl = slot + 1; sl < p.stat_slots; ++sl) dst[(size_t)(sl - slot) * p.Cout * 2] = 0;
+          }
+          epi_bar_sync();
+          for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
+        }
+      }
+    }
+    if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
+  } else if (FUSE_GN && warp < 4) {
+    // ------------------------------------------------------------------ GroupNorm + Swish transform
+    // thread -> (16-byte channel chunk j, pixel p = tt/8 + 16 i): its 8 channels' (scale, shift) stay
+    // in registers for the whole halo tile; a warp touches 4 full 128-byte pixel rows per access.
+    const int tt = threadIdx.x;
+    const int j = tt & 7;
+    const int p_first = tt >> 3;
+    const bool do_swish = p.gn_swish != 0;
+    int as = 0; uint32_t aphase = 0;
+    HDBG_DECL();
+    for (int sup = sup_begin; sup < sup_end; ++sup) {
+      Tile t[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
+      for (int sg = 0; sg < p.num_segs; ++sg) {
+        const HaloSeg seg = p.seg[sg];
+        for (int cb = 0; cb < seg.cblocks; ++cb) {
+          float sc[8], sh[8];
+          HDBG_T0();
+          if (seg.gn_off >= 0) {
+            // (scale, shift) pairs of this thread's 8 channels; all MT tiles lie in one image
+            const float4* g4 = reinterpret_cast<const float4*>(p.gn + (size_t)t[0].b * p.gn_C + seg.gn_off +
+                                                               cb * CONV_BLOCK_K + j * 8);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = __ldg(g4 + i);
+              sc[2 * i] = v.x; sh[2 * i] = v.y; sc[2 * i + 1] = v.z; sh[2 * i + 1] = v.w;
+            }
+            if (do_swish) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { sc[i] *= 0.5f; sh[i] *= 0.5f; }
+            }
+          }
+          ptx::mbar_wait(a_full(as), aphase);
+          HDBG_ACC(0);
+          HDBG_T0();
+          if (seg.gn_off >= 0 && !(p.ablate & 2)) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              // This thread's chunks sit 16 pixels (2048 B) apart; 16 = 0 (mod 8), so the swizzle term is
+              // the same for all of them. Loads are batched six deep: a lone warp per scheduler must
+              // cover LDS + MUFU latency with its own instruction-level parallelism.
+              uint8_t* tile = smem_gen + as * S::A_STAGE + m * HALO_STRIDE + p_first * 128 + ((j ^ (p_first & 7)) << 4);
+              const int gx0 = t[m].x0 - 1, gy0 = t[m].y0 - 1;
+              int hy = p_first / HALO_W, hx = p_first - hy * HALO_W;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                uint4 v[6];
+                bool ok[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  const int ci = half * 6 + i;
+                  ok[i] = (p_first + 16 * ci < HALO_W * HALO_H) && (unsigned)(gy0 + hy) < (unsigned)p.H &&
+                          (unsigned)(gx0 + hx) < (unsigned)p.W;
+                  v[i] = ok[i] ? *reinterpret_cast<const uint4*>(tile + ci * 2048) : make_uint4(0u, 0u, 0u, 0u);
+                  hx += 6; hy += 1;                       // + 16 pixels in a 10-wide tile
+                  if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  float f[8];
+                  unpack8(v[i], f);
+                  if (do_swish) {
+                    // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const float h = fmaf(f[e], sc[e], sh[e]);
+                      f[e] = fmaf(h, tanh_approx(h), h);
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+                  }
+                  if (ok[i]) *reinterpret_cast<uint4*>(tile + (half * 6 + i) * 2048) = pack8(f);
+                }
+              }
+            }
+            fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async reads
+          }
+          ptx::mbar_arrive(a_ready(as));
+          HDBG_ACC(1);
+          if (++as == AST) { as = 0; aphase ^= 1u; }
+        }
+      }
+    }
+    if (tt == 0) HDBG_FLUSH(10, 2);      // [10] transform waits A full (incl. table loads), [11] transforming
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 10) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
+}
+#endif  // __CUDACC__
+
+}  // namespace b200sr3

@@ -53,6 +53,14 @@ static void encode_weight_map(CUtensorMap* m, const bf16* w, int k_total, int co
     throw Error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
 }
 
+// shared with conv_halo.cu
+CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2) {
+  return encode_fn()(m, dt, rank, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <int BN, int ST, int MW>
@@ -75,6 +83,7 @@ void conv_init_device() {
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  conv_halo_init_device();
 }
 
 bool conv_can_fuse_stats(const Act& out, bool upsample2x) {

@@ -88,6 +88,7 @@ Engine::Engine(const b200sr3_config& cfg, int device) : cfg_(cfg), device_(devic
   if (const char* g = getenv("B200SR3_NO_GRAPH")) use_graph_ = !(g[0] == '1');
   if (const char* g = getenv("B200SR3_BLOCK_N")) force_block_n_ = atoi(g);
   if (const char* g = getenv("B200SR3_NO_FUSED_STATS")) fuse_stats_ = !(g[0] == '1');
+  if (const char* g = getenv("B200SR3_NO_HALO")) use_halo_ = !(g[0] == '1');
   build_layers();
 }
 
@@ -479,6 +480,37 @@ void Engine::build_workspace(Workspace& ws) {
     return y;
   };
 
+  // (scale, shift) table of a GroupNorm whose apply (+Swish) runs inside the consuming halo conv
+  auto gn_table = [&](const std::string& name, const Act& x0, const Act* x1, const std::string& gkey) {
+    auto g = std::make_shared<GnPlan>();
+    g->C0 = x0.C; g->stats0 = x0.stats; g->slots0 = x0.stat_slots;
+    g->C1 = x1 ? x1->C : 0; g->stats1 = x1 ? x1->stats : nullptr; g->slots1 = x1 ? x1->stat_slots : 1;
+    g->B = B; g->HW = x0.H * x0.W; g->groups = G;
+    const int C = g->C0 + g->C1;
+    REQUIRE(C % G == 0, "GroupNorm: channels not divisible by norm_groups");
+    g->gamma = T_(gkey + ".weight");
+    g->beta = T_(gkey + ".bias");
+    float2* tab = (float2*)dalloc((size_t)B * C * sizeof(float2));
+    ws.ops.push_back(Op{name + ".gn_scale", false, [g, tab](cudaStream_t s) { launch_gn_scale_shift(*g, tab, s); }, 0.0, 0.0});
+    return tab;
+  };
+  // halo-resident conv (conv_halo.cuh): 3x3 main source(s) with the GroupNorm+Swish applied in shared
+  // memory, raw 1x1 shortcut sources, GroupNorm statistics of the output from the epilogue
+  auto conv_halo = [&](const std::string& name, const std::vector<HaloSource>& srcs, bool up, const PackedConv& w,
+                       const float* bias, int bias_stride, const float2* gn, int gn_C, bool want_stats) {
+    const Act& a0 = srcs[0].act;
+    Act probe;
+    probe.B = B; probe.H = up ? 2 * a0.H : a0.H; probe.W = up ? 2 * a0.W : a0.W; probe.C = w.cout;
+    Act y = act(probe.H, probe.W, w.cout, want_stats ? conv_halo_stat_slots(probe, up) : 1);
+    ConvStats st;
+    st.partial = y.stats;
+    st.slots = y.stat_slots;
+    ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn, gn_C, true,
+                                       want_stats ? &st : nullptr));
+    ws.n_conv++;
+    return y;
+  };
+
   std::vector<Act> feats;
   Act cur;
   for (const LayerDesc& l : layers_) {
@@ -506,7 +538,10 @@ void Engine::build_workspace(Workspace& ws) {
       }
       case LayerKind::Up: {
         const PackedConv& pc = convs_.at(l.name + ".conv");
-        cur = conv(l.name, cur, 9, 1, true, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H * 2, cur.W * 2, true);
+        if (use_halo_ && conv_halo_eligible(cur.H, cur.W, cur.C % 64 == 0, pc.cout))
+          cur = conv_halo(l.name, {HaloSource{cur, 9, -1}}, true, pc, pc.bias, 0, nullptr, 0, true);
+        else
+          cur = conv(l.name, cur, 9, 1, true, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H * 2, cur.W * 2, true);
         break;
       }
       case LayerKind::Res: {
@@ -521,15 +556,31 @@ void Engine::build_workspace(Workspace& ws) {
         REQUIRE(cur.C == l.c_x, "internal: channel plan mismatch");
         const std::string rb = l.name + ".res_block";
         const Act xin = cur;
-        Act xn = group_norm(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0", true);
         const PackedConv& c1 = convs_.at(l.name + ".c1");
-        Act h = conv(l.name + ".conv1", xn, 9, 1, false, c1, nullptr, nullptr, table_ + noise_off_.at(l.name),
-                     noise_total_, nullptr, xin.H, xin.W, true);
-        Act hn = group_norm(l.name + ".block2", h, nullptr, rb + ".block2.block.0", true);
         const PackedConv& c2 = convs_.at(l.name + ".c2");
-        // the shortcut (res_conv 1x1, or identity) is one or two extra 1x1 K segments of this GEMM
-        cur = conv(l.name + ".conv2", hn, 9, 1, false, c2, &xin, is_up ? &skip : nullptr, c2.bias, 0, nullptr, xin.H,
-                   xin.W, true);
+        if (use_halo_ && conv_halo_eligible(xin.H, xin.W, (l.c_x % 64 == 0) && (l.c_skip % 64 == 0), l.cout)) {
+          // Block = GN -> Swish -> Conv (unet.py:80-91) as ONE kernel each: the GroupNorm apply runs on the
+          // halo tile in shared memory; only the tiny (scale, shift) table is a separate launch
+          const int cin = l.c_x + l.c_skip;
+          const float2* g1 = gn_table(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0");
+          std::vector<HaloSource> s1{HaloSource{xin, 9, 0}};
+          if (is_up) s1.push_back(HaloSource{skip, 9, l.c_x});
+          Act h = conv_halo(l.name + ".conv1", s1, false, c1, table_ + noise_off_.at(l.name), noise_total_, g1, cin,
+                            true);
+          const float2* g2 = gn_table(l.name + ".block2", h, nullptr, rb + ".block2.block.0");
+          // the shortcut (res_conv 1x1, or identity) is one or two extra raw 1x1 K segments of this GEMM
+          std::vector<HaloSource> s2{HaloSource{h, 9, 0}, HaloSource{xin, 1, -1}};
+          if (is_up) s2.push_back(HaloSource{skip, 1, -1});
+          cur = conv_halo(l.name + ".conv2", s2, false, c2, c2.bias, 0, g2, l.cout, true);
+        } else {
+          Act xn = group_norm(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0", true);
+          Act h = conv(l.name + ".conv1", xn, 9, 1, false, c1, nullptr, nullptr, table_ + noise_off_.at(l.name),
+                       noise_total_, nullptr, xin.H, xin.W, true);
+          Act hn = group_norm(l.name + ".block2", h, nullptr, rb + ".block2.block.0", true);
+          // the shortcut (res_conv 1x1, or identity) is one or two extra 1x1 K segments of this GEMM
+          cur = conv(l.name + ".conv2", hn, 9, 1, false, c2, &xin, is_up ? &skip : nullptr, c2.bias, 0, nullptr, xin.H,
+                     xin.W, true);
+        }
         if (l.attn) {
           const Act ain = cur;
           Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);

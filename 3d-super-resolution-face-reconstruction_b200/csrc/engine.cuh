@@ -10,6 +10,7 @@
 #include "../../include/b200sr3.h"
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "conv_halo.cuh"
 #include "kernels.cuh"
 
 namespace b200sr3 {
@@ -131,6 +132,7 @@ class Engine {
   cudaStream_t capture_stream_ = nullptr;
   bool use_graph_ = true;
   int force_block_n_ = 0;
+  bool use_halo_ = true;       // B200SR3_NO_HALO=1: first-generation conv + separate GroupNorm apply everywhere
   bool fuse_stats_ = true;     // B200SR3_NO_FUSED_STATS=1: GroupNorm statistics by chan_stats_kernel instead
 
   std::map<std::pair<int, int>, std::unique_ptr<Workspace>> workspaces_;
@@ -155,5 +157,18 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
                 const bf16* residual, const Act& out, int force_block_n, const ConvStats* stats);
 // Shared-memory opt-in for every conv kernel instance (once per process / device).
 void conv_init_device();
+
+// Halo-resident 3x3 conv with fused GroupNorm+Swish (conv_halo.cuh / conv_halo.cu).
+struct HaloSource {
+  Act act;
+  int ntaps = 9;      // 9: 3x3 main source (folded to 4 parity taps when upsample2x); 1: raw 1x1 shortcut source
+  int gn_off = -1;    // channel offset in the GroupNorm (scale, shift) table; < 0: no transform
+};
+bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout);
+int conv_halo_stat_slots(const Act& out, bool upsample2x);
+Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
+                     const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
+                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats);
+void conv_halo_init_device();
 
 }  // namespace b200sr3

@@ -162,6 +162,54 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(GnPlan g, int a
   for (; p < p_end; p += rows) emit(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), p);
 }
 
+// Same statistics code as gn_apply_kernel's preamble, for the fused path: one CTA per image.
+__global__ void __launch_bounds__(256) gn_scale_shift_kernel(GnPlan g, float2* __restrict__ out) {
+  __shared__ float chan[1024 * 2];
+  __shared__ float gstat[64 * 2];
+  const int C = g.C0 + g.C1;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  for (int c = tid; c < C; c += 256) {
+    const long long* sp;
+    int ns, cs;
+    if (c < g.C0) { sp = g.stats0 + ((size_t)b * g.slots0 * g.C0 + c) * 2; ns = g.slots0; cs = g.C0; }
+    else { sp = g.stats1 + ((size_t)b * g.slots1 * g.C1 + (c - g.C0)) * 2; ns = g.slots1; cs = g.C1; }
+    long long a = 0, d = 0;
+    for (int k = 0; k < ns; ++k) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(sp + (size_t)k * cs * 2);
+      a += v.x;
+      d += v.y;
+    }
+    chan[2 * c] = (float)((double)a * STAT_FIXED_INV);
+    chan[2 * c + 1] = (float)((double)d * STAT_FIXED_INV);
+  }
+  __syncthreads();
+  const int cg = C / g.groups;
+  if (tid < g.groups) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cg; ++k) { a += chan[2 * (tid * cg + k)]; d += chan[2 * (tid * cg + k) + 1]; }
+    const float inv_n = 1.0f / ((float)g.HW * (float)cg);
+    const float mean = a * inv_n;
+    const float var = fmaxf(d * inv_n - mean * mean, 0.f);
+    gstat[2 * tid] = mean;
+    gstat[2 * tid + 1] = rsqrtf(var + 1e-5f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    const int grp = c / cg;
+    const float sc = gstat[2 * grp + 1] * __ldg(g.gamma + c);
+    out[(size_t)b * C + c] = make_float2(sc, __ldg(g.beta + c) - gstat[2 * grp] * sc);
+  }
+}
+
+void launch_gn_scale_shift(const GnPlan& g, float2* out, cudaStream_t s) {
+  const int C = g.C0 + g.C1;
+  REQUIRE(C <= 1024 && C % g.groups == 0 && g.groups <= 64, "GroupNorm: unsupported channel count");
+  REQUIRE(g.stats0 && (g.C1 == 0 || g.stats1), "GroupNorm: missing channel statistics");
+  gn_scale_shift_kernel<<<g.B, 256, 0, s>>>(g, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 int chan_stats_chunks(int HW, int C) {
   long long per_img = (long long)HW * C;
   long long ch = per_img / ((long long)GN_THREADS * 8 * 16);   // ~16 vectors per thread

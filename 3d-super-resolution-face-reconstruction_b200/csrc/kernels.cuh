@@ -24,6 +24,11 @@ struct GnPlan {
 };
 void launch_gn_apply(const GnPlan& g, cudaStream_t s);
 
+// (scale, shift) table of a GroupNorm whose apply step is fused into the consuming conv
+// (conv_halo.cuh): out[b][c] = (rstd_g * gamma_c, beta_c - mean_g * rstd_g * gamma_c). Uses src0/src1
+// statistics, C0, C1, B, HW, groups, gamma, beta of the plan; src/dst pointers are ignored.
+void launch_gn_scale_shift(const GnPlan& g, float2* out, cudaStream_t s);
+
 struct ChanStatsPlan {
   const bf16* src = nullptr;     // [B,H,W,C]
   int B = 0, HW = 0, C = 0;

@@ -144,6 +144,21 @@ B200SR3_API int b200sr3_conv2d(int device, const float* x, const float* w, const
                    const float* residual, int B, int Cin, int H, int W, int Cout, int k,
                    int stride, int upsample2x, float* y, int iters, float* avg_ms, void* stream);
 
+/* Kernel-level entry for the halo-resident conv (csrc/conv_halo.cuh), used by the parity tests and
+ * tools/conv_bench.py: y = conv3x3([swish](GroupNorm(cat(x0, x1)))) + bias + conv1x1(cat(r0, r1)),
+ * i.e. one reference Block (unet.py:80-91: GN -> Swish -> Conv) with the ResnetBlock shortcut
+ * (unet.py:103-110) folded in as extra K segments, and the channel concat of unet.py:261 read as
+ * two sources. x0/x1/r0/r1: fp32 NCHW [B,C*,H,W] (x1, r0, r1 optional: pass NULL and 0 channels);
+ * gamma/beta: [C0+C1] or NULL for no GroupNorm; w: OIHW [Cout,C0+C1,3,3]; wres: [Cout,Cr0+Cr1,1,1];
+ * upsample2x applies nearest 2x to the (un-normalised) input first (unet.py:58-65, no GN, no
+ * shortcut). stats_out (optional): [B][Cout][2] per-(image, channel) sum and sum of squares of y as
+ * the fused GroupNorm statistics report them. H % 16 == 0, W % 8 == 0, W >= 16, channels % 64 == 0. */
+B200SR3_API int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int C1,
+                   const float* gamma, const float* beta, int groups, int swish, const float* w,
+                   const float* bias, const float* r0, int Cr0, const float* r1, int Cr1,
+                   const float* wres, int B, int H, int W, int Cout, int upsample2x, float* y,
+                   float* stats_out, int iters, float* avg_ms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
