@@ -134,6 +134,21 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
   p.out = out.ptr;
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
+  // output maps for the epilogue's tensor stores: box = one warp's slab (64 channels x 8 x 4 pixels);
+  // a folded upsample writes output parity (py, px) through a view with doubled pixel strides
+  for (int par = 0; par < p.num_par; ++par) {
+    const int sc = upsample2x ? 2 : 1;
+    const int py = par >> 1, px = par & 1;
+    bf16* base = out.ptr + ((size_t)py * out.W + px) * out.C;
+    cuuint64_t dims[4] = {(cuuint64_t)out.C, (cuuint64_t)(out.W / sc), (cuuint64_t)(out.H / sc), (cuuint64_t)out.B};
+    cuuint64_t strides[3] = {(cuuint64_t)sc * out.C * 2, (cuuint64_t)sc * out.W * out.C * 2,
+                             (cuuint64_t)out.H * out.W * out.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_TW, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_tiled(&p.o_map[par], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(output) failed with CUresult " + std::to_string((int)r));
+  }
 
   // ---- (BLOCK_N, MT): lowest modelled time. Per 64-channel block a super tile costs
   // max(MMA cycles, L2->SM bytes / rate); a CTA runs ceil(super tiles / SMs) of them.

@@ -23,11 +23,18 @@
 // stream through their own ring, one [BLOCK_N x 64] tile per (tap, block). A CTA processes MT
 // horizontally adjacent tiles against each weight tile (MT x fewer weight bytes from L2).
 //
-// Warp roles (384 threads): 0-3 = GroupNorm/Swish transform, 4-7 = epilogue (TMEM -> +bias[t] -> bf16
-// NHWC stores, GroupNorm statistics of the output), 8 = halo TMA producer, 9 = weight TMA producer,
-// 10 = TMEM allocator, 11 = MMA issuer. The single-thread roles carry the HIGHEST warp ids on purpose:
-// a scheduler (warp id % 4) prefers its highest-numbered ready warp, and with the issuer below the
-// ALU-heavy transform / epilogue warps the tensor pipe starved whenever those were busy.
+// Warp roles (512 threads): 0-3 and 8-11 = GroupNorm/Swish transform, 4-7 = epilogue, 12 = halo TMA
+// producer, 13 = weight TMA producer, 14 = TMEM allocator, 15 = MMA issuer. The single-thread roles
+// carry the HIGHEST warp ids on purpose: a scheduler (warp id % 4) prefers its highest-numbered ready
+// warp, and with the issuer below the ALU-heavy transform / epilogue warps the tensor pipe starved.
+//
+// Epilogue: each of the four warps owns 32 accumulator rows = a 4-row x 8-pixel slab of the tile. Per
+// 64 output channels it moves TMEM -> registers -> (+bias[t], bf16) -> a 4 KB 128B-swizzled staging slab
+// in shared memory, hands the slab to a TMA tensor store (asynchronous, fully coalesced; the four
+// output parities of a folded upsample are four strided tensor maps) and forms the GroupNorm statistics
+// of the output from the slab: lane l adds up columns 2l, 2l+1 over the slab's 32 rows (conflict-free
+// LDS.32), i.e. the cross-row reduction costs no shuffles. Statistics are those of the bf16-rounded
+// tensor - exactly what the consumer normalises - and accumulate as int64 fixed point.
 #pragma once
 #include "conv_umma.cuh"
 
@@ -37,7 +44,7 @@ constexpr int HALO_W = 10, HALO_H = 18;                  // (8+2) x (16+2) pixel
 constexpr int HALO_TW = 8, HALO_TH = 16;                 // output tile
 constexpr int HALO_BYTES = HALO_W * HALO_H * 128;        // 23040: what one TMA box load delivers
 constexpr int HALO_STRIDE = 23552;                       // rounded up to the 1024 B swizzle period
-constexpr int HALO_THREADS = 384;
+constexpr int HALO_THREADS = 512;
 constexpr int HALO_A_STAGES = 3;
 constexpr int HALO_MAX_SEGS = 4;
 
@@ -53,6 +60,7 @@ struct HaloSeg {
 struct alignas(64) ConvHaloParams {
   CUtensorMap a_map[HALO_MAX_SEGS];
   CUtensorMap w_map;
+  CUtensorMap o_map[4];            // output, box (64 ch, 8, 4, 1); one per output parity when num_par == 4
   HaloSeg seg[HALO_MAX_SEGS];
   int num_segs;
   int num_par;                     // 1, or 4 (folded nearest-2x upsample: output parity (y&1, x&1))
@@ -83,16 +91,30 @@ struct HaloSmem {
   static constexpr int A_STAGE = MT * HALO_STRIDE;
   static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
   static constexpr int W_STAGE = BLOCK_N * 128;
-  static constexpr int STAT_BYTES = 4 * 2 * BLOCK_N * 8;
+  static constexpr int NSTG = BLOCK_N == 256 ? 1 : 2;            // staging slabs per epilogue warp
+  static constexpr int STG_BYTES = 4 * NSTG * 4096;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
-  static constexpr int W_FIT = (BUDGET - A_BYTES - STAT_BYTES) / W_STAGE;
+  static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES) / W_STAGE;
   static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
   static constexpr int W_OFFSET = A_BYTES;
-  static constexpr int STAT_OFFSET = W_OFFSET + W_STAGES * W_STAGE;
-  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+  static constexpr int STG_OFFSET = W_OFFSET + W_STAGES * W_STAGE;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static_assert(W_STAGES >= 3, "weight ring too shallow");
+  static_assert(BLOCK_N * 16 <= 4096, "statistics hand-over must fit one slab");
 };
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // MUFU.TANH: max relative error 2^-11, far below the bf16 rounding of the value it produces
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -129,7 +151,6 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  long long* sstat = reinterpret_cast<long long*>(smem_gen + S::STAT_OFFSET);
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
   // barriers: a_full[AST], a_ready[AST], a_empty[AST], w_full[WST], w_empty[WST], tmem_full[2], tmem_empty[2]
   auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -145,14 +166,15 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     ptx::prefetch_tmap(&p.w_map);
     for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
+    for (int i = 0; i < p.num_par; ++i) ptx::prefetch_tmap(&p.o_map[i]);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == 13 && lane == 0) {
     for (int s = 0; s < AST; ++s) {
       ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_ready(s), 128);
+      ptx::mbar_init(a_ready(s), 256);
       ptx::mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < WST; ++s) {
@@ -165,7 +187,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 10) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  if (warp == 14) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -187,7 +209,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     return t;
   };
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- halo producer
       int as = 0; uint32_t aphase = 0;
@@ -215,7 +237,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (p.dbg) { hd[1] = (unsigned long long)(clock64() - hd_start); hd[2] = (unsigned long long)(sup_end - sup_begin); }
       HDBG_FLUSH(0, 3);      // [0] A producer waits a_empty, [1] total, [2] super tiles
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- weight producer
       int ws = 0; uint32_t wphase = 0;
@@ -236,7 +258,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == 15) {
     // ------------------------------------------------------------------ MMA issuer
     // One elected thread runs the whole loop. A single thread retires dependent scalar instructions at
     // ~5 cycles each while an N=64 MMA occupies the tensor pipe for only 48 cycles, so the loop is kept
@@ -308,19 +330,22 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue
+    constexpr int NCH = BLOCK_N / 64;
+    constexpr int NSTG = S::NSTG;
     const int wq = warp & 3;
-    const int row = wq * 32 + lane;
     const int tid_e = threadIdx.x - 128;
-    const int lx = row & 7, ly = row >> 3;
+    const uint32_t slab_u32 = smem_base + S::STG_OFFSET + wq * (NSTG * 4096);
+    uint8_t* slab_gen = smem_gen + S::STG_OFFSET + wq * (NSTG * 4096);
     const bool do_stats = p.stat_partial != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
-    const int osc = p.num_par == 4 ? 2 : 1;
-    long long* sacc = sstat + wq * (2 * BLOCK_N);
-    if (do_stats)
-      for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
+    long long acc[NCH][4];          // this lane's columns (2l, 2l+1) of each 64-channel chunk: sum0, sum1, sq0, sq1
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+    // where lane l finds columns (2l, 2l+1) of slab row r: chunk (l >> 2) ^ (r & 7), word l & 3
+    const uint32_t col_chunk = (uint32_t)(lane >> 2), col_word = (uint32_t)(lane & 3) * 4u;
 
-    int it = 0;
+    int it = 0, stg = 0;
     HDBG_DECL();
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
@@ -329,85 +354,111 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       ptx::mbar_wait(tmem_full(buf), use & 1u);
       HDBG_ACC(0);
       ptx::tc_fence_after();
-      Tile t0 = decode(sup, 0);
+      const Tile t0 = decode(sup, 0);
       const int n0 = t0.n_tile * BLOCK_N;
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const Tile t = decode(sup, m);
-        const int y = t.y0 + ly, x = t.x0 + lx;
-        const size_t pix = ((size_t)t.b * p.out_H + (size_t)(y * osc + (t.par >> 1))) * p.out_W +
-                           (size_t)(x * osc + (t.par & 1));
-        bf16* out_row = p.out + pix * p.Cout + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          if (!(p.ablate & 16)) {
-            ptx::tmem_ld32(taddr + (uint32_t)c0, v);
-            ptx::tmem_ld_wait();
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(c0 + j);
-          }
-          float f[32];
+        for (int cc = 0; cc < NCH; ++cc) {
+          const uint32_t sl = slab_u32 + (uint32_t)stg * 4096u;
+          uint8_t* slg = slab_gen + stg * 4096;
+          // the tensor store that last read this slab must have finished reading it
+          if (lane == 0) bulk_wait_read<NSTG - 1>();
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (bias) {
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            if (!(p.ablate & 16)) {
+              ptx::tmem_ld32(taddr + (uint32_t)(cc * 64 + half * 32), v);
+              ptx::tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+              for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(half * 32 + j);
             }
-          }
-          if (!(p.ablate & 1)) {
+            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc * 64 + half * 32 + j));
+                f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(slg + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(f + 8 * j);
+          }
+          fence_proxy_async_smem();       // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0 && !(p.ablate & 1)) {
+            tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
+            bulk_commit();
           }
           if (do_stats && !(p.ablate & 32)) {
-            float q[32];
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
-            const float s_sum = warp_transpose_sum(f, lane);
-            const float s_sq = warp_transpose_sum(q, lane);
-            sacc[c0 + lane] += __float2ll_rn(s_sum * STAT_FIXED_SCALE);
-            sacc[BLOCK_N + c0 + lane] += __float2ll_rn(s_sq * STAT_FIXED_SCALE);
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(slg + r * 128 + (((col_chunk ^ (uint32_t)(r & 7)) << 4) | col_word));
+              const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+              s0 += lo; q0 = fmaf(lo, lo, q0);
+              s1 += hi; q1 = fmaf(hi, hi, q1);
+            }
+            acc[cc][0] += __float2ll_rn(s0 * STAT_FIXED_SCALE);
+            acc[cc][1] += __float2ll_rn(s1 * STAT_FIXED_SCALE);
+            acc[cc][2] += __float2ll_rn(q0 * STAT_FIXED_SCALE);
+            acc[cc][3] += __float2ll_rn(q1 * STAT_FIXED_SCALE);
           }
+          stg = (stg + 1 == NSTG) ? 0 : stg + 1;
         }
       }
+      // all of this thread's TMEM reads have completed: hand the accumulator back to the MMA warp
       ptx::tc_fence_before();
       ptx::mbar_arrive(tmem_empty(buf));
 
       if (do_stats) {
         const int seg = sup / p.seg_len_super;
         if (sup + 1 == sup_end || (sup + 1) / p.seg_len_super != seg) {
-          // the CTA's run over this (n tile, image) segment ends: publish its partial sums
+          // the CTA's run over this (n tile, image) segment ends: publish its partial sums. The four
+          // warps' sums meet in the (drained) staging slabs: [column][sum|sq] int64 per warp.
           const long long G = gridDim.x, T = p.total_super;
           const int first_cta = (int)((((long long)seg * p.seg_len_super + 1) * G - 1) / T);
           const int last_cta = (int)((((long long)(seg + 1) * p.seg_len_super) * G - 1) / T);
           const int slot = (int)blockIdx.x - first_cta;
-          epi_bar_sync();
-          for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
-            const int col = item % BLOCK_N;
-            const int st = item / BLOCK_N;
-            long long a = 0;
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          long long* mine = reinterpret_cast<long long*>(slab_gen);
 #pragma unroll
-            for (int ww = 0; ww < 4; ++ww) a += sstat[(ww * 2 + st) * BLOCK_N + col];
-            long long* dst = p.stat_partial + (((size_t)t0.b * p.stat_slots + slot) * p.Cout + (n0 + col)) * 2 + st;
-            *dst = a;
-            if ((int)blockIdx.x == last_cta)
-              for (int sl = slot + 1; sl < p.stat_slots; ++sl) dst[(size_t)(sl - slot) * p.Cout * 2] = 0;
+          for (int cc = 0; cc < NCH; ++cc) {
+            const int col = cc * 64 + 2 * lane;
+            *reinterpret_cast<longlong2*>(mine + col * 2) = make_longlong2(acc[cc][0], acc[cc][2]);
+            *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(acc[cc][1], acc[cc][3]);
+            acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0;
           }
           epi_bar_sync();
-          for (int i = lane; i < 2 * BLOCK_N; i += 32) sacc[i] = 0;
+          for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
+            long long a = 0;
+#pragma unroll
+            for (int ww = 0; ww < 4; ++ww)
+              a += reinterpret_cast<const long long*>(smem_gen + S::STG_OFFSET + ww * (NSTG * 4096))[item];
+            long long* dst = p.stat_partial + (((size_t)t0.b * p.stat_slots + slot) * p.Cout + n0) * 2 + item;
+            *dst = a;
+            if ((int)blockIdx.x == last_cta)
+              for (int sl2 = slot + 1; sl2 < p.stat_slots; ++sl2) dst[(size_t)(sl2 - slot) * p.Cout * 2] = 0;
+          }
+          epi_bar_sync();
         }
       }
     }
+    if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
-  } else if (FUSE_GN && warp < 4) {
+  } else if (FUSE_GN && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
     // thread -> (16-byte channel chunk j, pixel p = tt/8 + 16 i): its 8 channels' (scale, shift) stay
     // in registers for the whole halo tile; a warp touches 4 full 128-byte pixel rows per access.
-    const int tt = threadIdx.x;
+    const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;      // 0..255
     const int j = tt & 7;
     const int p_first = tt >> 3;
     const bool do_swish = p.gn_swish != 0;
@@ -442,42 +493,38 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           if (seg.gn_off >= 0 && !(p.ablate & 2)) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-              // This thread's chunks sit 16 pixels (2048 B) apart; 16 = 0 (mod 8), so the swizzle term is
-              // the same for all of them. Loads are batched six deep: a lone warp per scheduler must
+              // This thread's chunks sit 32 pixels (4096 B) apart; 32 = 0 (mod 8), so the swizzle term is
+              // the same for all of them. All (up to) six loads are issued before any math: a warp must
               // cover LDS + MUFU latency with its own instruction-level parallelism.
               uint8_t* tile = smem_gen + as * S::A_STAGE + m * HALO_STRIDE + p_first * 128 + ((j ^ (p_first & 7)) << 4);
               const int gx0 = t[m].x0 - 1, gy0 = t[m].y0 - 1;
               int hy = p_first / HALO_W, hx = p_first - hy * HALO_W;
+              uint4 v[6];
+              bool ok[6];
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                uint4 v[6];
-                bool ok[6];
+              for (int i = 0; i < 6; ++i) {
+                ok[i] = (p_first + 32 * i < HALO_W * HALO_H) && (unsigned)(gy0 + hy) < (unsigned)p.H &&
+                        (unsigned)(gx0 + hx) < (unsigned)p.W;
+                v[i] = ok[i] ? *reinterpret_cast<const uint4*>(tile + i * 4096) : make_uint4(0u, 0u, 0u, 0u);
+                hx += 2; hy += 3;                       // + 32 pixels in a 10-wide tile
+                if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
+              }
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                  const int ci = half * 6 + i;
-                  ok[i] = (p_first + 16 * ci < HALO_W * HALO_H) && (unsigned)(gy0 + hy) < (unsigned)p.H &&
-                          (unsigned)(gx0 + hx) < (unsigned)p.W;
-                  v[i] = ok[i] ? *reinterpret_cast<const uint4*>(tile + ci * 2048) : make_uint4(0u, 0u, 0u, 0u);
-                  hx += 6; hy += 1;                       // + 16 pixels in a 10-wide tile
-                  if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
-                }
+              for (int i = 0; i < 6; ++i) {
+                float f[8];
+                unpack8(v[i], f);
+                if (do_swish) {
+                  // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                  float f[8];
-                  unpack8(v[i], f);
-                  if (do_swish) {
-                    // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float h = fmaf(f[e], sc[e], sh[e]);
-                      f[e] = fmaf(h, tanh_approx(h), h);
-                    }
-                  } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+                  for (int e = 0; e < 8; ++e) {
+                    const float h = fmaf(f[e], sc[e], sh[e]);
+                    f[e] = fmaf(h, tanh_approx(h), h);
                   }
-                  if (ok[i]) *reinterpret_cast<uint4*>(tile + (half * 6 + i) * 2048) = pack8(f);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
                 }
+                if (ok[i]) *reinterpret_cast<uint4*>(tile + i * 4096) = pack8(f);
               }
             }
             fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async reads
@@ -493,7 +540,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 10) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
+  if (warp == 14) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
 }
 #endif  // __CUDACC__
 
