@@ -84,6 +84,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return q;
 }
+// ---- Philox4x32-10 + Box-Muller: the sampler's own noise stream (keyed by pixel, timestep, seed)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+// The reference's update, op for op (diffusion.py:150-151, 175-176, 159-160, 186-187).
+__device__ __forceinline__ float posterior_update(float x, float eps, float z, float a, float bc,
+                                                  float c1, float c2, float sigma) {
+  float x0 = __fsub_rn(__fmul_rn(a, x), __fmul_rn(bc, eps));
+  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
+  return __fadd_rn(mean, __fmul_rn(z, sigma));
+}
 #endif
 
 }  // namespace b200sr3

@@ -25,6 +25,8 @@ void conv_halo_init_device() {
   set_attr<128, 1, false>(); set_attr<128, 1, true>();
   set_attr<128, 2, false>(); set_attr<128, 2, true>();
   set_attr<256, 1, false>(); set_attr<256, 1, true>();
+  set_attr<16, 1, false>();  set_attr<16, 1, true>();
+  set_attr<16, 2, false>();  set_attr<16, 2, true>();
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -69,7 +71,8 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
 
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
-                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats) {
+                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
+                     std::shared_ptr<ConvHaloParams>* params_out) {
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
   const int PH = a0.H, PW = a0.W;
@@ -80,7 +83,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   REQUIRE(out.B == a0.B && out.H == (upsample2x ? 2 : 1) * PH && out.W == (upsample2x ? 2 : 1) * PW,
           "halo conv: output shape mismatch");
   REQUIRE(PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16, "halo conv: unsupported spatial size");
-  REQUIRE(out.C == w.cout && out.C % 64 == 0, "halo conv: Cout must be a multiple of 64");
+  if (tail) {
+    REQUIRE(out.C == 16 && w.cout == 16 && tail->oc >= 1 && tail->oc <= 4 && !upsample2x && !(stats && stats->partial),
+            "halo conv: the tail is a plain 3x3 conv with <= 4 output channels padded to 16");
+  } else {
+    REQUIRE(out.C == w.cout && out.C % 64 == 0, "halo conv: Cout must be a multiple of 64");
+  }
 
   // ---- segments; K order of the packed weights: [tap][all main channels] then the 1x1 shortcut blocks
   int c_main = 0;
@@ -136,7 +144,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
   // output maps for the epilogue's tensor stores: box = one warp's slab (64 channels x 8 x 4 pixels);
   // a folded upsample writes output parity (py, px) through a view with doubled pixel strides
-  for (int par = 0; par < p.num_par; ++par) {
+  if (tail) {
+    p.tail_x = tail->x; p.tail_eps = tail->eps_out; p.coefs = tail->coefs; p.tail_oc = tail->oc;
+  }
+  for (int par = 0; par < p.num_par && !tail; ++par) {
     const int sc = upsample2x ? 2 : 1;
     const int py = par >> 1, px = par & 1;
     bf16* base = out.ptr + ((size_t)py * out.W + px) * out.C;
@@ -160,11 +171,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     if (const char* e = getenv("B200SR3_HALO_BN")) fbn = atoi(e);
     if (const char* e = getenv("B200SR3_HALO_MT")) fmt = atoi(e);
     double best = 1e30;
-    const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};
+    const int cand[7][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}, {16, 2}, {16, 1}};
     for (auto& c : cand) {
+      if ((c[0] == 16) != (tail != nullptr)) continue;
       if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
       if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
-      const double mma_cyc = c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : 48.0);   // per MMA, measured
+      const double mma_cyc = c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : (c[0] == 64 ? 48.0 : 36.0));   // per MMA, measured
       double per_super = 0.0;
       for (int i = 0; i < p.num_segs; ++i) {
         const double mma = p.seg[i].ntaps * c[1] * 4 * mma_cyc;
@@ -208,15 +220,18 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     const double m = (double)out.B * out.H * out.W;
     double k = 0;
     for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
-    op.flops = 2.0 * m * (double)out.C * k;
+    op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
   }
   op.run = [pp, grid, bn, mt, any_gn](cudaStream_t s) {
     if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
     else if (bn == 128 && mt == 2) launch_halo<128, 2>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);
-    else if (mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);
-    else launch_halo<64, 1>(*pp, any_gn, grid, s);
+    else if (bn == 64 && mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);
+    else if (bn == 64) launch_halo<64, 1>(*pp, any_gn, grid, s);
+    else if (mt == 2) launch_halo<16, 2>(*pp, any_gn, grid, s);
+    else launch_halo<16, 1>(*pp, any_gn, grid, s);
   };
+  if (params_out) *params_out = pp;
   return op;
 }
 

@@ -78,6 +78,13 @@ struct alignas(64) ConvHaloParams {
   int gn_swish;
   long long* stat_partial;         // as ConvParams::stat_partial
   int stat_slots;
+  // BLOCK_N == 16 ("tail"): the conv is final_conv (unet.py:233, Cout = out_channel <= 4 padded to 16) and
+  // the epilogue applies the sampler update (diffusion.py:144-187) to the fp32 NCHW state instead of
+  // storing an activation: eps -> x0 = clamp(A x - B eps) -> mean -> + sigma z.
+  float* tail_x;                   // fp32 NCHW [B][tail_oc][H][W], updated in place (null: eps only)
+  float* tail_eps;                 // optional fp32 NCHW eps output
+  const float* coefs;              // [5][T]: A, Bc, C1, C2, LV
+  int tail_oc;
   // measurement only (B200SR3_CONV_ABLATE bit mask; results are then wrong): 1 = no global stores,
   // 2 = transform arrives without touching the tile, 16 = no TMEM loads, 32 = no statistics math
   int ablate;
@@ -91,7 +98,7 @@ struct HaloSmem {
   static constexpr int A_STAGE = MT * HALO_STRIDE;
   static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
   static constexpr int W_STAGE = BLOCK_N * 128;
-  static constexpr int NSTG = BLOCK_N == 256 ? 1 : 2;            // staging slabs per epilogue warp
+  static constexpr int NSTG = BLOCK_N == 256 ? 1 : 2;            // staging slabs per epilogue warp (unused by the tail)
   static constexpr int STG_BYTES = 4 * NSTG * 4096;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES) / W_STAGE;
@@ -108,6 +115,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -328,9 +344,74 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
       HDBG_FLUSH(4, 3);      // [4] MMA waits A ready, [5] waits W full, [6] waits TMEM empty
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (BLOCK_N == 16 && warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ tail epilogue: sampler update
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int lx = row & 7, ly = row >> 3;
+    const int OC = p.tail_oc;
+    const size_t plane = (size_t)p.H * p.W;
+    float a = 0.f, bc = 0.f, c1 = 0.f, c2 = 0.f, sigma = 0.f;
+    int ts = 0, T = 0, mode = 0;
+    if (p.tail_x) {
+      ts = p.ctl->t; T = p.ctl->T; mode = p.ctl->noise_mode;
+      a = p.coefs[ts]; bc = p.coefs[T + ts]; c1 = p.coefs[2 * T + ts]; c2 = p.coefs[3 * T + ts];
+      sigma = expf(0.5f * p.coefs[4 * T + ts]);
+    }
+    int it = 0;
+    HDBG_DECL();
+    for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      HDBG_T0();
+      ptx::mbar_wait(tmem_full(buf), use & 1u);
+      HDBG_ACC(0);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const Tile t = decode(sup, m);
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N), v);
+        ptx::tmem_ld_wait();
+        const int y = t.y0 + ly, x = t.x0 + lx;
+        const size_t base = (size_t)t.b * OC * plane + (size_t)y * p.W + x;
+        const long long pix = ((long long)t.b * p.H + y) * p.W + x;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.tail_x && ts > 0) {
+          if (mode == 1 || mode == 3) {
+            const float* zp = p.ctl->noise;
+            if (zp) {
+              if (mode == 1) zp += (size_t)(T - ts) * (size_t)p.ctl->numel;
+#pragma unroll
+              for (int o = 0; o < 4; ++o) if (o < OC) z[o] = __ldg(zp + base + o * plane);
+            }
+          } else if (mode == 2) {
+            const unsigned long long seed = p.ctl->seed;
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+            z[0] = g0.x; z[1] = g0.y; z[2] = g1.x; z[3] = g1.y;
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          if (o < OC) {
+            const float eps = __uint_as_float(v[o]) + (p.bias ? __ldg(p.bias + o) : 0.f);
+            if (p.tail_eps) p.tail_eps[base + o * plane] = eps;
+            if (p.tail_x) {
+              const float xv = p.tail_x[base + o * plane];
+              p.tail_x[base + o * plane] = posterior_update(xv, eps, z[o], a, bc, c1, c2, sigma);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty(buf));
+    }
+    if (threadIdx.x == 128) HDBG_FLUSH(8, 1);
+  } else if (BLOCK_N != 16 && warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue
-    constexpr int NCH = BLOCK_N / 64;
+    constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
     constexpr int NSTG = S::NSTG;
     const int wq = warp & 3;
     const int tid_e = threadIdx.x - 128;

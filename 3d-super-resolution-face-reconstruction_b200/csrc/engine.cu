@@ -299,6 +299,15 @@ void Engine::finalize_weights(cudaStream_t s) {
       case LayerKind::Final: {
         tail_w_ = (float*)dalloc((size_t)l.cout * 9 * l.c_x * sizeof(float));
         launch_pack_tail_weight(T_(l.name + ".block.3.weight"), tail_w_, l.cout, l.c_x, s);
+        if (l.c_x % CONV_BLOCK_K == 0 && l.cout <= 4) {
+          // the same conv as a tensor-core operand: rows >= out_channel are zero
+          tail_pc_ = PackedConv();
+          tail_pc_.cout = 16; tail_pc_.taps = 9; tail_pc_.cin_main = l.c_x; tail_pc_.k_total = 9 * l.c_x;
+          tail_pc_.w = (bf16*)dalloc((size_t)16 * tail_pc_.k_total * sizeof(bf16));
+          CUDA_CHECK(cudaMemsetAsync(tail_pc_.w, 0, (size_t)16 * tail_pc_.k_total * sizeof(bf16), s));
+          launch_pack_conv_weight(T_(l.name + ".block.3.weight"), tail_pc_.w, l.cout, l.c_x, 9, l.c_x, 0,
+                                  tail_pc_.k_total, s);
+        }
         break;
       }
       case LayerKind::Res: {
@@ -598,6 +607,19 @@ void Engine::build_workspace(Workspace& ws) {
         break;
       }
       case LayerKind::Final: {
+        if (use_halo_ && tail_pc_.w && conv_halo_eligible(cur.H, cur.W, cur.C % 64 == 0, 64)) {
+          // final_conv = Block(GN -> Swish -> Conv 64 -> 3) + the sampler update as ONE halo conv launch
+          const float2* g = gn_table(l.name, cur, nullptr, l.name + ".block.0");
+          Act o16;
+          o16.B = B; o16.H = cur.H; o16.W = cur.W; o16.C = 16;
+          HaloTail tl;
+          tl.x = ws.x; tl.eps_out = nullptr; tl.coefs = coefs_; tl.oc = oc;
+          ws.ops.push_back(make_conv_halo_op(l.name + ".tail", {HaloSource{cur, 9, 0}}, false, tail_pc_,
+                                             T_(l.name + ".block.3.bias"), 0, ctl_, o16, g, cur.C, true, nullptr, &tl,
+                                             &ws.tail_halo));
+          ws.n_conv++;
+          break;
+        }
         Act fn = group_norm(l.name, cur, nullptr, l.name + ".block.0", true);
         auto tp = std::make_shared<TailPlan>();
         tp->src = fn.ptr; tp->w = tail_w_; tp->bias = T_(l.name + ".block.3.bias");
@@ -628,8 +650,7 @@ void Engine::run_ops(Workspace& ws, cudaStream_t s) {
 void Engine::ensure_graph(Workspace& ws) {
   if (ws.graph || !use_graph_) return;
   // The tail must be in "update" mode while capturing (plans are read at launch = capture time).
-  ws.tail_plan->eps_out = nullptr;
-  ws.tail_plan->x = ws.x;
+  ws.set_tail(ws.x, nullptr);
   cudaGraph_t g = nullptr;
   CUDA_CHECK(cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal));
   try {
@@ -656,8 +677,7 @@ int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, do
   const size_t numel = (size_t)B * cfg_.out_channel * R * R;
   launch_philox_fill(ws.x, B, cfg_.out_channel, R, 1234, T_sched_, s);
   write_ctl(T_sched_ - 1, B200SR3_NOISE_PHILOX, nullptr, 1234, (long long)numel, s);
-  ws.tail_plan->eps_out = nullptr;
-  ws.tail_plan->x = ws.x;
+  ws.set_tail(ws.x, nullptr);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
   for (int rep = 0; rep < 2; ++rep) {          // first repetition warms up
@@ -702,11 +722,9 @@ void Engine::unet_forward(const float* cond, const float* x, float noise_level, 
                     cfg_.inner_channel, noise_total_, table_};
   launch_noise_table(np, T_sched_, 1, s);
   write_ctl(T_sched_, 0, nullptr, 0, 0, s);
-  ws.tail_plan->eps_out = ws.eps;
-  ws.tail_plan->x = nullptr;
+  ws.set_tail(nullptr, ws.eps);
   run_ops(ws, s);
-  ws.tail_plan->eps_out = nullptr;
-  ws.tail_plan->x = ws.x;
+  ws.set_tail(ws.x, nullptr);
   CUDA_CHECK(cudaMemcpyAsync(eps, ws.eps, img, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
@@ -724,8 +742,7 @@ void Engine::step(const float* cond, const float* x_t, const float* noise, int t
   if (cond) CUDA_CHECK(cudaMemcpyAsync(ws.cond, cond, img, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(ws.x, x_t, img, cudaMemcpyDeviceToDevice, s));
   write_ctl(t, 3, noise, 0, (long long)(img / sizeof(float)), s);
-  ws.tail_plan->eps_out = nullptr;
-  ws.tail_plan->x = ws.x;
+  ws.set_tail(ws.x, nullptr);
   run_ops(ws, s);
   CUDA_CHECK(cudaMemcpyAsync(x_tm1, ws.x, img, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -754,8 +771,7 @@ void Engine::sample(const float* cond, int noise_mode, const float* noise, uint6
     launch_philox_fill(ws.x, B, cfg_.out_channel, R, seed, T, s);
   }
   write_ctl(T - 1, noise_mode, noise, seed, (long long)numel, s);
-  ws.tail_plan->eps_out = nullptr;
-  ws.tail_plan->x = ws.x;
+  ws.set_tail(ws.x, nullptr);
   const int inter = 1 | (T / 10);
   int snap = 0;
   for (int t = T - 1; t >= 0; --t) {

@@ -63,8 +63,14 @@ struct Workspace {
   float* x = nullptr;      // fp32 NCHW sampler state
   float* eps = nullptr;    // fp32 NCHW (unet_forward output)
   std::vector<Op> ops;     // one UNet forward + update, in order
-  TailPlan* tail = nullptr;   // points into the closure-owned plan of the last op
+  // the last op (final conv + sampler update) writes either the updated state or eps; exactly one of
+  // the two plans is live and the launch closure reads it at launch time
   std::shared_ptr<TailPlan> tail_plan;
+  std::shared_ptr<ConvHaloParams> tail_halo;
+  void set_tail(float* x, float* eps) {
+    if (tail_plan) { tail_plan->x = x; tail_plan->eps_out = eps; }
+    if (tail_halo) { tail_halo->tail_x = x; tail_halo->tail_eps = eps; }
+  }
   std::map<std::string, Act> layer_out;
   cudaGraphExec_t graph = nullptr;
   int64_t n_conv = 0;
@@ -121,6 +127,7 @@ class Engine {
   std::map<std::string, int> noise_off_;          // layer -> column offset in the bias table
   int noise_total_ = 0;
   float *head_w_ = nullptr, *tail_w_ = nullptr;
+  PackedConv tail_pc_;        // final_conv as a 16-row bf16 GEMM operand (halo conv tail)
   float *wall_ = nullptr, *ball_ = nullptr;
   std::vector<void*> owned_;
 
@@ -166,9 +173,16 @@ struct HaloSource {
 };
 bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout);
 int conv_halo_stat_slots(const Act& out, bool upsample2x);
+struct HaloTail {      // final_conv fused with the sampler update (conv_halo.cuh, BLOCK_N == 16)
+  float* x = nullptr;          // fp32 NCHW state, updated in place (null: eps only)
+  float* eps_out = nullptr;    // optional fp32 NCHW eps
+  const float* coefs = nullptr;
+  int oc = 3;
+};
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
-                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats);
+                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats,
+                     const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr);
 void conv_halo_init_device();
 
 }  // namespace b200sr3
