@@ -13,10 +13,10 @@ CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, v
 
 static int g_halo_sms = 148;
 
-template <int BN, int MT, bool GN>
+template <int BN, int MT, bool GN, int GEO = 0>
 static void set_attr() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  HaloSmem<BN, MT>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, GN, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<BN, MT, GEO>::TOTAL));
 }
 
 void conv_halo_init_device() {
@@ -27,20 +27,25 @@ void conv_halo_init_device() {
   set_attr<256, 1, false>(); set_attr<256, 1, true>();
   set_attr<16, 1, false>();  set_attr<16, 1, true>();
   set_attr<16, 2, false>();  set_attr<16, 2, true>();
+  set_attr<64, 1, false, 1>();  set_attr<64, 1, true, 1>();
+  set_attr<128, 1, false, 1>(); set_attr<128, 1, true, 1>();
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int GEO = 0>
 static void launch_halo(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
-  if (gn) conv_halo_kernel<BN, MT, true><<<grid, HALO_THREADS, HaloSmem<BN, MT>::TOTAL, s>>>(p);
-  else conv_halo_kernel<BN, MT, false><<<grid, HALO_THREADS, HaloSmem<BN, MT>::TOTAL, s>>>(p);
+  if (gn) conv_halo_kernel<BN, MT, true, GEO><<<grid, HALO_THREADS, HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
+  else conv_halo_kernel<BN, MT, false, GEO><<<grid, HALO_THREADS, HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
 
+static bool geo1(int H, int W) { return H == 8 && W == 8; }   // two whole 8x8 images per tile
+
 bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout) {
-  return c_multiple_of_64_all && (cout % 64 == 0) && (H % HALO_TH == 0) && (W % HALO_TW == 0) && W >= 16 && H >= 16;
+  if (!c_multiple_of_64_all || cout % 64 != 0) return false;
+  return geo1(H, W) || ((H % HALO_TH == 0) && (W % HALO_TW == 0) && W >= 16 && H >= 16);
 }
 
 // CTAs a (n tile, image) segment of seg_len_super super tiles can be spread over when total_super
@@ -57,12 +62,14 @@ static int slots_needed(long long seg_len_super, long long total_super, long lon
 
 int conv_halo_stat_slots(const Act& out, bool upsample2x) {
   const int PH = upsample2x ? out.H / 2 : out.H, PW = upsample2x ? out.W / 2 : out.W;
-  const long long seg_len = (long long)(PH / HALO_TH) * (PW / HALO_TW) * (upsample2x ? 4 : 1);
+  const bool g1 = geo1(PH, PW);
+  const long long seg_len = (g1 ? 1 : (long long)(PH / HALO_TH) * (PW / HALO_TW)) * (upsample2x ? 4 : 1);
+  const long long units = g1 ? (out.B + 1) / 2 : out.B;
   int need = 1;
   for (int mt = 1; mt <= 2; ++mt) {
     if (seg_len % mt) continue;
     for (int tn = 1; tn <= 16; tn *= 2) {
-      const long long total = seg_len / mt * out.B * tn;
+      const long long total = seg_len / mt * units * tn;
       need = std::max(need, slots_needed(seg_len / mt, total, std::min<long long>(total, g_halo_sms)));
     }
   }
@@ -82,7 +89,9 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.num_par = upsample2x ? 4 : 1;
   REQUIRE(out.B == a0.B && out.H == (upsample2x ? 2 : 1) * PH && out.W == (upsample2x ? 2 : 1) * PW,
           "halo conv: output shape mismatch");
-  REQUIRE(PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16, "halo conv: unsupported spatial size");
+  const bool g1 = geo1(PH, PW);
+  REQUIRE(g1 || (PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16), "halo conv: unsupported spatial size");
+  REQUIRE(!(g1 && tail), "halo conv: the tail runs on the one-image geometry");
   if (tail) {
     REQUIRE(out.C == 16 && w.cout == 16 && tail->oc >= 1 && tail->oc <= 4 && !upsample2x && !(stats && stats->partial),
             "halo conv: the tail is a plain 3x3 conv with <= 4 output channels padded to 16");
@@ -107,6 +116,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
     cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
+    if (g1) {      // (C, W, B, H)-ordered view, box = 10 x 2 images x 10
+      std::swap(dims[2], dims[3]);
+      std::swap(strides[1], strides[2]);
+      box[2] = 2; box[3] = 10;
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode_tiled(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.ptr, dims, strides, box, estr,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -135,12 +149,14 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.num_segs = (int)srcs.size();
   REQUIRE(k_short == w.k_total, "halo conv: packed weight K does not match the segment list");
   REQUIRE(w.up_folded == upsample2x, "halo conv: weight packing / upsample mismatch");
-  p.tiles_w = PW / HALO_TW;
-  p.tiles_h = PH / HALO_TH;
+  p.tiles_w = g1 ? 1 : PW / HALO_TW;
+  p.tiles_h = g1 ? 1 : PH / HALO_TH;
+  p.units = g1 ? (out.B + 1) / 2 : out.B;
   p.B = out.B; p.H = PH; p.W = PW; p.Cout = out.C;
   p.out_H = out.H; p.out_W = out.W;
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
   p.out = out.ptr;
+  REQUIRE(!any_gn || gn_C <= 1024, "halo conv: the fused GroupNorm handles at most 1024 channels");
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
   // output maps for the epilogue's tensor stores: box = one warp's slab (64 channels x 8 x 4 pixels);
   // a folded upsample writes output parity (py, px) through a view with doubled pixel strides
@@ -155,6 +171,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     cuuint64_t strides[3] = {(cuuint64_t)sc * out.C * 2, (cuuint64_t)sc * out.W * out.C * 2,
                              (cuuint64_t)out.H * out.W * out.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_TW, 4, 1};
+    if (g1) {      // (C, W, B, H)-ordered view; a warp's slab is 8 x 2 images x 2 rows
+      std::swap(dims[2], dims[3]);
+      std::swap(strides[1], strides[2]);
+      box[2] = 2; box[3] = 2;
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode_tiled(&p.o_map[par], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
@@ -164,7 +185,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   // ---- (BLOCK_N, MT): lowest modelled time. Per 64-channel block a super tile costs
   // max(MMA cycles, L2->SM bytes / rate); a CTA runs ceil(super tiles / SMs) of them.
   const long long tiles_img = (long long)p.tiles_w * p.tiles_h;
-  const long long m_tiles = tiles_img * p.num_par * out.B;
+  const long long m_tiles = tiles_img * p.num_par * p.units;
   int bn = 0, mt = 0;
   {
     int fbn = 0, fmt = 0;
@@ -174,13 +195,14 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     const int cand[7][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}, {16, 2}, {16, 1}};
     for (auto& c : cand) {
       if ((c[0] == 16) != (tail != nullptr)) continue;
+      if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
       if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
       const double mma_cyc = c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : (c[0] == 64 ? 48.0 : 36.0));   // per MMA, measured
       double per_super = 0.0;
       for (int i = 0; i < p.num_segs; ++i) {
         const double mma = p.seg[i].ntaps * c[1] * 4 * mma_cyc;
-        const double bytes = c[1] * (double)HALO_BYTES + p.seg[i].ntaps * c[0] * 128.0;
+        const double bytes = c[1] * (double)(g1 ? 25600 : HALO_BYTES) + p.seg[i].ntaps * c[0] * 128.0;
         per_super += p.seg[i].cblocks * std::max(mma, bytes / 56.0);
       }
       per_super += 300.0 + c[1] * c[0] * 5.0;                                      // epilogue drain, not overlapped at the end
@@ -222,8 +244,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
   }
-  op.run = [pp, grid, bn, mt, any_gn](cudaStream_t s) {
-    if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
+  op.run = [pp, grid, bn, mt, any_gn, g1](cudaStream_t s) {
+    if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
+    else if (g1) launch_halo<64, 1, 1>(*pp, any_gn, grid, s);
+    else if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
     else if (bn == 128 && mt == 2) launch_halo<128, 2>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);
     else if (bn == 64 && mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);

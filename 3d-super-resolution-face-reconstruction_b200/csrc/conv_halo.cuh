@@ -48,6 +48,18 @@ constexpr int HALO_THREADS = 512;
 constexpr int HALO_A_STAGES = 3;
 constexpr int HALO_MAX_SEGS = 4;
 
+// Tile geometry. GEO 0: an 8 x 16 pixel tile of one image, halo 10 x 18. GEO 1 (8 x 8 images): a tile is
+// TWO whole images laid side by side in the halo tile - pixel (hy, image, hx) at hy*20 + image*10 + hx,
+// fetched by one TMA box over a (C, W, B, H)-ordered view - so that the 8-row groups (one image row of
+// one image each, ordered y-major, image-minor) are again exactly 10 pixels apart.
+template <int GEO> struct HaloGeo;
+template <> struct HaloGeo<0> {
+  static constexpr int PITCH = 10, ROWS = 18, NPIX = 180, BYTES = 180 * 128, STRIDE = 23552, IMGS = 1;
+};
+template <> struct HaloGeo<1> {
+  static constexpr int PITCH = 20, ROWS = 10, NPIX = 200, BYTES = 200 * 128, STRIDE = 26624, IMGS = 2;
+};
+
 struct HaloSeg {
   int map;           // a_map index
   int cblocks;       // 64-channel blocks of this source
@@ -66,6 +78,7 @@ struct alignas(64) ConvHaloParams {
   int num_par;                     // 1, or 4 (folded nearest-2x upsample: output parity (y&1, x&1))
   int tiles_w, tiles_h;            // 8x16 tiles per image over the pixel space the tiles walk
   int B, H, W, Cout;               // pixel space the tiles walk (the SOURCE grid when num_par == 4)
+  int units;                       // images (GEO 0) or image pairs (GEO 1) the tile index walks
   int out_H, out_W;
   int tiles_n, total_super;        // N tiles; super tiles (MT tiles each) in the launch
   int seg_len_super;               // super tiles per (n tile, image) = tiles_w*tiles_h*num_par/MT
@@ -93,22 +106,24 @@ struct alignas(64) ConvHaloParams {
 };
 
 #ifdef __CUDACC__
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int GEO = 0>
 struct HaloSmem {
-  static constexpr int A_STAGE = MT * HALO_STRIDE;
+  static constexpr int A_STAGE = MT * HaloGeo<GEO>::STRIDE;
   static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
   static constexpr int W_STAGE = BLOCK_N * 128;
-  static constexpr int NSTG = BLOCK_N == 256 ? 1 : 2;            // staging slabs per epilogue warp (unused by the tail)
+  static constexpr int NSTG = (BLOCK_N == 256 || (BLOCK_N == 128 && MT == 2)) ? 1 : 2;   // staging slabs per epilogue warp
   static constexpr int STG_BYTES = 4 * NSTG * 4096;
+  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 8;  // (scale, shift) of the current image (pair), <= 1024 channels
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
-  static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES) / W_STAGE;
+  static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
   static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
   static constexpr int W_OFFSET = A_BYTES;
   static constexpr int STG_OFFSET = W_OFFSET + W_STAGES * W_STAGE;
-  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int GN_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int BAR_OFFSET = GN_OFFSET + GN_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static_assert(W_STAGES >= 3, "weight ring too shallow");
-  static_assert(BLOCK_N * 16 <= 4096, "statistics hand-over must fit one slab");
+  static_assert(BLOCK_N * 16 * HaloGeo<GEO>::IMGS <= 4096, "statistics hand-over must fit one slab");
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -157,10 +172,12 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
 #define HDBG_ACC(i) do { if (p.dbg) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
 #define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
-template <int BLOCK_N, int MT, bool FUSE_GN>
+template <int BLOCK_N, int MT, bool FUSE_GN, int GEO>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
-  using S = HaloSmem<BLOCK_N, MT>;
+  using S = HaloSmem<BLOCK_N, MT, GEO>;
+  using G = HaloGeo<GEO>;
+  static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the two-image geometry runs plain convs, one tile at a time");
   constexpr int AST = HALO_A_STAGES, WST = S::W_STAGES;
   constexpr int NBUF = 2;
   static_assert(NBUF * MT * BLOCK_N <= 512, "TMEM budget");
@@ -220,8 +237,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     t.x0 = (tile % p.tiles_w) * HALO_TW; tile /= p.tiles_w;
     t.y0 = (tile % p.tiles_h) * HALO_TH; tile /= p.tiles_h;
     t.par = tile % p.num_par; tile /= p.num_par;
-    t.b = tile % p.B;
-    t.n_tile = tile / p.B;
+    t.b = (tile % p.units) * G::IMGS;
+    t.n_tile = tile / p.units;
     return t;
   };
 
@@ -241,11 +258,16 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             HDBG_T0();
             ptx::mbar_wait(a_empty(as), aphase ^ 1u);
             HDBG_ACC(0);
-            ptx::mbar_expect_tx(a_full(as), MT * HALO_BYTES);
+            ptx::mbar_expect_tx(a_full(as), MT * G::BYTES);
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-              ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * HALO_STRIDE, &p.a_map[seg.map], a_full(as),
-                               cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
+            for (int m = 0; m < MT; ++m) {
+              if (GEO == 0)
+                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
+                                 cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
+              else      // view ordered (C, W, B, H): both images of the pair in one box
+                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
+                                 cb * CONV_BLOCK_K, -1, t[m].b, -1);
+            }
             if (++as == AST) { as = 0; aphase ^= 1u; }
           }
         }
@@ -306,7 +328,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const int ntaps = p.seg[sg].ntaps, cblocks = p.seg[sg].cblocks;
           const int ntx = ntaps == 9 ? 3 : (ntaps == 4 ? 2 : 1);
-          const uint32_t pix0 = ntaps == 9 ? 0u : (ntaps == 4 ? (uint32_t)((par >> 1) * HALO_W + (par & 1)) : (uint32_t)(HALO_W + 1));
+          const uint32_t pix0 = ntaps == 9 ? 0u : (ntaps == 4 ? (uint32_t)((par >> 1) * G::PITCH + (par & 1)) : (uint32_t)(G::PITCH + 1));
           for (int cb = 0; cb < cblocks; ++cb) {
             HDBG_T0();
             ptx::mbar_wait(FUSE_GN ? a_ready(as) : a_full(as), aphase);
@@ -328,13 +350,13 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (HALO_STRIDE >> 4) + 2 * k), A_HI),
+                  ptx::umma_bf16(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (G::STRIDE >> 4) + 2 * k), A_HI),
                                  desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
               }
               ptx::umma_commit(wcur);
               accum = 1;
               a_lo += 8u;
-              if (++tx == ntx) { tx = 0; a_lo += (uint32_t)(HALO_W - ntx) * 8u; }
+              if (++tx == ntx) { tx = 0; a_lo += (uint32_t)(G::PITCH - ntx) * 8u; }
             }
             ptx::umma_commit(a_empty(as));
             if (++as == AST) { as = 0; aphase ^= 1u; }
@@ -420,9 +442,13 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const bool do_stats = p.stat_partial != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
-    long long acc[NCH][4];          // this lane's columns (2l, 2l+1) of each 64-channel chunk: sum0, sum1, sq0, sq1
+    constexpr int IMGS = G::IMGS;
+    // this lane's columns (2l, 2l+1) of each 64-channel chunk, per image of the tile: sum0, sum1, sq0, sq1
+    long long acc[IMGS][NCH][4];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+    for (int im = 0; im < IMGS; ++im)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc[im][c][0] = acc[im][c][1] = acc[im][c][2] = acc[im][c][3] = 0;
     // where lane l finds columns (2l, 2l+1) of slab row r: chunk (l >> 2) ^ (r & 7), word l & 3
     const uint32_t col_chunk = (uint32_t)(lane >> 2), col_word = (uint32_t)(lane & 3) * 4u;
 
@@ -475,22 +501,29 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           fence_proxy_async_smem();       // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0 && !(p.ablate & 1)) {
-            tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
+            if (GEO == 0) tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
+            else tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, 0, t.b, 2 * wq);      // (C, W, B, H) view
             bulk_commit();
           }
           if (do_stats && !(p.ablate & 32)) {
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            float s0[IMGS], s1[IMGS], q0[IMGS], q1[IMGS];
+#pragma unroll
+            for (int im = 0; im < IMGS; ++im) s0[im] = s1[im] = q0[im] = q1[im] = 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
+              const int im = (IMGS == 2) ? ((r >> 3) & 1) : 0;      // GEO 1: 8-row groups alternate between the images
               const uint32_t w = *reinterpret_cast<const uint32_t*>(slg + r * 128 + (((col_chunk ^ (uint32_t)(r & 7)) << 4) | col_word));
               const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
-              s0 += lo; q0 = fmaf(lo, lo, q0);
-              s1 += hi; q1 = fmaf(hi, hi, q1);
+              s0[im] += lo; q0[im] = fmaf(lo, lo, q0[im]);
+              s1[im] += hi; q1[im] = fmaf(hi, hi, q1[im]);
             }
-            acc[cc][0] += __float2ll_rn(s0 * STAT_FIXED_SCALE);
-            acc[cc][1] += __float2ll_rn(s1 * STAT_FIXED_SCALE);
-            acc[cc][2] += __float2ll_rn(q0 * STAT_FIXED_SCALE);
-            acc[cc][3] += __float2ll_rn(q1 * STAT_FIXED_SCALE);
+#pragma unroll
+            for (int im = 0; im < IMGS; ++im) {
+              acc[im][cc][0] += __float2ll_rn(s0[im] * STAT_FIXED_SCALE);
+              acc[im][cc][1] += __float2ll_rn(s1[im] * STAT_FIXED_SCALE);
+              acc[im][cc][2] += __float2ll_rn(q0[im] * STAT_FIXED_SCALE);
+              acc[im][cc][3] += __float2ll_rn(q1[im] * STAT_FIXED_SCALE);
+            }
           }
           stg = (stg + 1 == NSTG) ? 0 : stg + 1;
         }
@@ -512,19 +545,23 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           __syncwarp();
           long long* mine = reinterpret_cast<long long*>(slab_gen);
 #pragma unroll
-          for (int cc = 0; cc < NCH; ++cc) {
-            const int col = cc * 64 + 2 * lane;
-            *reinterpret_cast<longlong2*>(mine + col * 2) = make_longlong2(acc[cc][0], acc[cc][2]);
-            *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(acc[cc][1], acc[cc][3]);
-            acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0;
-          }
+          for (int im = 0; im < IMGS; ++im)
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+              const int col = im * BLOCK_N + cc * 64 + 2 * lane;
+              *reinterpret_cast<longlong2*>(mine + col * 2) = make_longlong2(acc[im][cc][0], acc[im][cc][2]);
+              *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(acc[im][cc][1], acc[im][cc][3]);
+              acc[im][cc][0] = acc[im][cc][1] = acc[im][cc][2] = acc[im][cc][3] = 0;
+            }
           epi_bar_sync();
-          for (int item = tid_e; item < 2 * BLOCK_N; item += 128) {
+          for (int item = tid_e; item < IMGS * 2 * BLOCK_N; item += 128) {
+            const int im = item / (2 * BLOCK_N), within = item - im * 2 * BLOCK_N;
+            if (t0.b + im >= p.B) continue;            // odd batch: the pair's second image does not exist
             long long a = 0;
 #pragma unroll
             for (int ww = 0; ww < 4; ++ww)
               a += reinterpret_cast<const long long*>(smem_gen + S::STG_OFFSET + ww * (NSTG * 4096))[item];
-            long long* dst = p.stat_partial + (((size_t)t0.b * p.stat_slots + slot) * p.Cout + n0) * 2 + item;
+            long long* dst = p.stat_partial + (((size_t)(t0.b + im) * p.stat_slots + slot) * p.Cout + n0) * 2 + within;
             *dst = a;
             if ((int)blockIdx.x == last_cta)
               for (int sl2 = slot + 1; sl2 < p.stat_slots; ++sl2) dst[(size_t)(sl2 - slot) * p.Cout * 2] = 0;
@@ -537,35 +574,49 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
   } else if (FUSE_GN && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
-    // thread -> (16-byte channel chunk j, pixel p = tt/8 + 16 i): its 8 channels' (scale, shift) stay
-    // in registers for the whole halo tile; a warp touches 4 full 128-byte pixel rows per access.
+    // thread -> (16-byte channel chunk j, pixels p_first + 32 i): its 8 channels' (scale, shift) sit in
+    // registers for the whole halo tile; a warp touches 4 full 128-byte pixel rows per access. The
+    // (scale, shift) table of the current image (pair) is staged in shared memory once, so a stage does
+    // not start with an L2 round trip.
+    constexpr int IMGS = G::IMGS;
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;      // 0..255
     const int j = tt & 7;
     const int p_first = tt >> 3;
     const bool do_swish = p.gn_swish != 0;
+    float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C], halved if swish
+    int tab_b = -1;
     int as = 0; uint32_t aphase = 0;
     HDBG_DECL();
     for (int sup = sup_begin; sup < sup_end; ++sup) {
       Tile t[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
+      if (p.gn && t[0].b != tab_b) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous table
+        for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
+          const int im = idx >= p.gn_C ? 1 : 0;
+          const int c = idx - im * p.gn_C;
+          float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
+          if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
+          gtab[idx] = v;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        tab_b = t[0].b;
+      }
       for (int sg = 0; sg < p.num_segs; ++sg) {
         const HaloSeg seg = p.seg[sg];
         for (int cb = 0; cb < seg.cblocks; ++cb) {
-          float sc[8], sh[8];
+          float sc[IMGS][8], sh[IMGS][8];
           HDBG_T0();
           if (seg.gn_off >= 0) {
-            // (scale, shift) pairs of this thread's 8 channels; all MT tiles lie in one image
-            const float4* g4 = reinterpret_cast<const float4*>(p.gn + (size_t)t[0].b * p.gn_C + seg.gn_off +
-                                                               cb * CONV_BLOCK_K + j * 8);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 v = __ldg(g4 + i);
-              sc[2 * i] = v.x; sh[2 * i] = v.y; sc[2 * i + 1] = v.z; sh[2 * i + 1] = v.w;
-            }
-            if (do_swish) {
+            for (int im = 0; im < IMGS; ++im) {
+              const float4* g4 = reinterpret_cast<const float4*>(gtab + im * p.gn_C + seg.gn_off + cb * CONV_BLOCK_K + j * 8);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { sc[i] *= 0.5f; sh[i] *= 0.5f; }
+              for (int i = 0; i < 4; ++i) {
+                const float4 v = g4[i];
+                sc[im][2 * i] = v.x; sh[im][2 * i] = v.y; sc[im][2 * i + 1] = v.z; sh[im][2 * i + 1] = v.w;
+              }
             }
           }
           ptx::mbar_wait(a_full(as), aphase);
@@ -574,38 +625,47 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           if (seg.gn_off >= 0 && !(p.ablate & 2)) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-              // This thread's chunks sit 32 pixels (4096 B) apart; 32 = 0 (mod 8), so the swizzle term is
-              // the same for all of them. All (up to) six loads are issued before any math: a warp must
-              // cover LDS + MUFU latency with its own instruction-level parallelism.
-              uint8_t* tile = smem_gen + as * S::A_STAGE + m * HALO_STRIDE + p_first * 128 + ((j ^ (p_first & 7)) << 4);
+              // GEO 0: chunks 32 pixels apart cover the 180-pixel halo (the ring belongs to neighbouring
+              // tiles or is zero padding). GEO 1: only the 2 x 64 image pixels are visited - the ring is
+              // all padding. All loads are issued before any math: a warp must cover LDS + MUFU latency
+              // with its own instruction-level parallelism.
+              constexpr int NCHK = GEO == 0 ? (G::NPIX + 31) / 32 : 4;
+              uint8_t* tile = smem_gen + as * S::A_STAGE + m * G::STRIDE;
               const int gx0 = t[m].x0 - 1, gy0 = t[m].y0 - 1;
-              int hy = p_first / HALO_W, hx = p_first - hy * HALO_W;
-              uint4 v[6];
-              bool ok[6];
+              uint4 v[NCHK];
+              uint4* ptr[NCHK];
+              bool ok[NCHK];
+              int img[NCHK];
 #pragma unroll
-              for (int i = 0; i < 6; ++i) {
-                ok[i] = (p_first + 32 * i < HALO_W * HALO_H) && (unsigned)(gy0 + hy) < (unsigned)p.H &&
-                        (unsigned)(gx0 + hx) < (unsigned)p.W;
-                v[i] = ok[i] ? *reinterpret_cast<const uint4*>(tile + i * 4096) : make_uint4(0u, 0u, 0u, 0u);
-                hx += 2; hy += 3;                       // + 32 pixels in a 10-wide tile
-                if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
+              for (int i = 0; i < NCHK; ++i) {
+                int px;
+                if (GEO == 0) {
+                  px = p_first + 32 * i;
+                  const int hy = px / G::PITCH, hx = px - hy * G::PITCH;
+                  img[i] = 0;
+                  ok[i] = px < G::NPIX && (unsigned)(gy0 + hy) < (unsigned)p.H && (unsigned)(gx0 + hx) < (unsigned)p.W;
+                } else {
+                  const int q = p_first + 32 * i;                       // (y, image, x) = (q >> 4, (q >> 3) & 1, q & 7)
+                  img[i] = (q >> 3) & 1;
+                  px = ((q >> 4) + 1) * G::PITCH + img[i] * 10 + (q & 7) + 1;
+                  ok[i] = t[m].b + img[i] < p.B;
+                }
+                ptr[i] = reinterpret_cast<uint4*>(tile + px * 128 + ((j ^ (px & 7)) << 4));
+                v[i] = ok[i] ? *ptr[i] : make_uint4(0u, 0u, 0u, 0u);
               }
 #pragma unroll
-              for (int i = 0; i < 6; ++i) {
+              for (int i = 0; i < NCHK; ++i) {
                 float f[8];
                 unpack8(v[i], f);
-                if (do_swish) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float scv = (IMGS == 2 && img[i]) ? sc[IMGS - 1][e] : sc[0][e];
+                  const float shv = (IMGS == 2 && img[i]) ? sh[IMGS - 1][e] : sh[0][e];
+                  const float h = fmaf(f[e], scv, shv);
                   // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float h = fmaf(f[e], sc[e], sh[e]);
-                    f[e] = fmaf(h, tanh_approx(h), h);
-                  }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+                  f[e] = do_swish ? fmaf(h, tanh_approx(h), h) : h;
                 }
-                if (ok[i]) *reinterpret_cast<uint4*>(tile + i * 4096) = pack8(f);
+                if (ok[i]) *ptr[i] = pack8(f);
               }
             }
             fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async reads

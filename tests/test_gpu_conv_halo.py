@@ -27,6 +27,10 @@ CASES = [
     (3, 128, 0, 128, 0, 64, 64, 128, 1, 0),
     (2, 128, 0, 0, 0, 16, 16, 128, 0, 1),           # folded nearest-2x upsample, 16 -> 32
     (1, 64, 0, 0, 0, 32, 16, 128, 1, 0),            # non-square
+    (4, 512, 0, 512, 0, 8, 8, 512, 1, 0),           # 8x8 images: two images per tile
+    (3, 128, 64, 128, 64, 8, 8, 128, 1, 0),         # ... odd batch: the last pair is half empty
+    (5, 64, 0, 0, 0, 8, 8, 64, 0, 0),
+    (3, 128, 0, 0, 0, 8, 8, 128, 0, 1),             # folded upsample 8 -> 16
 ]
 SHAPES = [(0, 0), (64, 1), (64, 2), (128, 1), (128, 2), (256, 1)]
 
@@ -145,7 +149,7 @@ def test_block_properties_at_baseline_size():
 
 def test_block_rejects_bad_shapes():
     from b200sr3 import _lib
-    x = torch.zeros(1, 64, 8, 8, device="cuda")         # below the 8x16 tile
+    x = torch.zeros(1, 64, 4, 4, device="cuda")         # below every tile geometry
     w = torch.zeros(64, 64, 3, 3, device="cuda")
     b = torch.zeros(64, device="cuda")
     with pytest.raises(_lib.B200Error):

@@ -26,6 +26,11 @@ SHAPES = [
     ("c1 512+256->256 @32", 512, 256, 0, 0, 32, 256, 0),
     ("c1 512->512 @16", 512, 0, 0, 0, 16, 512, 0),
     ("c1 512+512->512 @16", 512, 512, 0, 0, 16, 512, 0),
+    ("c1 512->512 @8", 512, 0, 0, 0, 8, 512, 0),
+    ("c2 512->512+id @8", 512, 0, 512, 0, 8, 512, 0),
+    ("c1 512+512->512 @8", 512, 512, 0, 0, 8, 512, 0),
+    ("c2 512->512+res1024 @8", 512, 0, 512, 512, 8, 512, 0),
+    ("up 512->512 @8->16", 512, 0, 0, 0, 8, 512, 1),
     ("up 128->128 @64->128", 128, 0, 0, 0, 64, 128, 1),
     ("up 256->256 @32->64", 256, 0, 0, 0, 32, 256, 1),
     ("up 512->512 @16->32", 512, 0, 0, 0, 16, 512, 1),
