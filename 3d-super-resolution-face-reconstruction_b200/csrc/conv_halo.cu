@@ -23,7 +23,6 @@ void conv_halo_init_device() {
   set_attr<64, 1, false>();  set_attr<64, 1, true>();
   set_attr<64, 2, false>();  set_attr<64, 2, true>();
   set_attr<128, 1, false>(); set_attr<128, 1, true>();
-  set_attr<128, 2, false>(); set_attr<128, 2, true>();
   set_attr<256, 1, false>(); set_attr<256, 1, true>();
   set_attr<16, 1, false>();  set_attr<16, 1, true>();
   set_attr<16, 2, false>();  set_attr<16, 2, true>();
@@ -36,8 +35,8 @@ void conv_halo_init_device() {
 
 template <int BN, int MT, int GEO = 0>
 static void launch_halo(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
-  if (gn) conv_halo_kernel<BN, MT, true, GEO><<<grid, HALO_THREADS, HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
-  else conv_halo_kernel<BN, MT, false, GEO><<<grid, HALO_THREADS, HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
+  if (gn) conv_halo_kernel<BN, MT, true, GEO><<<grid, halo_threads(BN), HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
+  else conv_halo_kernel<BN, MT, false, GEO><<<grid, halo_threads(BN), HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -192,7 +191,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     if (const char* e = getenv("B200SR3_HALO_BN")) fbn = atoi(e);
     if (const char* e = getenv("B200SR3_HALO_MT")) fmt = atoi(e);
     double best = 1e30;
-    const int cand[7][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}, {16, 2}, {16, 1}};
+    const int cand[6][2] = {{256, 1}, {128, 1}, {64, 2}, {64, 1}, {16, 2}, {16, 1}};
     for (auto& c : cand) {
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
@@ -248,7 +247,6 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
     else if (g1) launch_halo<64, 1, 1>(*pp, any_gn, grid, s);
     else if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
-    else if (bn == 128 && mt == 2) launch_halo<128, 2>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);
     else if (bn == 64 && mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);
     else if (bn == 64) launch_halo<64, 1>(*pp, any_gn, grid, s);

@@ -44,7 +44,11 @@ constexpr int HALO_W = 10, HALO_H = 18;                  // (8+2) x (16+2) pixel
 constexpr int HALO_TW = 8, HALO_TH = 16;                 // output tile
 constexpr int HALO_BYTES = HALO_W * HALO_H * 128;        // 23040: what one TMA box load delivers
 constexpr int HALO_STRIDE = 23552;                       // rounded up to the 1024 B swizzle period
-constexpr int HALO_THREADS = 512;
+// Epilogue warp sets (alternating 64-channel units). Measured on B200: a second set does not pay - the
+// BLOCK_N = 64 layers are bound by shared-memory bandwidth (UMMA operand reads + TMA writes + transform
+// + staging = ~370 KB per tile at 128 B/clk), not by epilogue issue slots - so every shape runs one set.
+constexpr int halo_esets(int block_n) { return (void)block_n, 1; }
+constexpr int halo_threads(int block_n) { return 512 + 128 * (halo_esets(block_n) - 1); }
 constexpr int HALO_A_STAGES = 3;
 constexpr int HALO_MAX_SEGS = 4;
 
@@ -99,7 +103,8 @@ struct alignas(64) ConvHaloParams {
   const float* coefs;              // [5][T]: A, Bc, C1, C2, LV
   int tail_oc;
   // measurement only (B200SR3_CONV_ABLATE bit mask; results are then wrong): 1 = no global stores,
-  // 2 = transform arrives without touching the tile, 16 = no TMEM loads, 32 = no statistics math
+  // 2 = transform arrives without touching the tile, 4 = no weight loads, 8 = no halo loads,
+  // 16 = no TMEM loads, 32 = no statistics math
   int ablate;
   // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv_block): [grid][16] cycle counters
   unsigned long long* dbg;
@@ -111,8 +116,9 @@ struct HaloSmem {
   static constexpr int A_STAGE = MT * HaloGeo<GEO>::STRIDE;
   static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
   static constexpr int W_STAGE = BLOCK_N * 128;
-  static constexpr int NSTG = (BLOCK_N == 256 || (BLOCK_N == 128 && MT == 2)) ? 1 : 2;   // staging slabs per epilogue warp
-  static constexpr int STG_BYTES = 4 * NSTG * 4096;
+  static constexpr int NSTG = (BLOCK_N == 256 || MT == 2) ? 1 : 2;   // staging slabs per epilogue warp
+  static constexpr int ESETS = halo_esets(BLOCK_N);
+  static constexpr int STG_BYTES = 4 * ESETS * NSTG * 4096;
   static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 8;  // (scale, shift) of the current image (pair), <= 1024 channels
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
@@ -173,11 +179,15 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
 #define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
 template <int BLOCK_N, int MT, bool FUSE_GN, int GEO>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+__global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   using S = HaloSmem<BLOCK_N, MT, GEO>;
   using G = HaloGeo<GEO>;
   static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the two-image geometry runs plain convs, one tile at a time");
+  constexpr int ESETS = S::ESETS;
+  // warp groups: 0 = transform A, 1 = epilogue A, 2 = transform B, [3 = epilogue B], last = single-thread roles
+  constexpr int LW = 4 * (2 + ESETS);        // first warp of the last group: LW+0 halo producer, +1 weight producer,
+                                              // +2 TMEM allocator, +3 MMA issuer
   constexpr int AST = HALO_A_STAGES, WST = S::W_STAGES;
   constexpr int NBUF = 2;
   static_assert(NBUF * MT * BLOCK_N <= 512, "TMEM budget");
@@ -199,12 +209,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 12 && lane == 0) {
+  if (warp == LW && lane == 0) {
     ptx::prefetch_tmap(&p.w_map);
     for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
     for (int i = 0; i < p.num_par; ++i) ptx::prefetch_tmap(&p.o_map[i]);
   }
-  if (warp == 13 && lane == 0) {
+  if (warp == LW + 1 && lane == 0) {
     for (int s = 0; s < AST; ++s) {
       ptx::mbar_init(a_full(s), 1);
       ptx::mbar_init(a_ready(s), 256);
@@ -216,11 +226,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     for (int b = 0; b < NBUF; ++b) {
       ptx::mbar_init(tmem_full(b), 1);
-      ptx::mbar_init(tmem_empty(b), 128);
+      ptx::mbar_init(tmem_empty(b), 128 * ESETS);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 14) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  if (warp == LW + 2) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -242,7 +252,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     return t;
   };
 
-  if (warp == 12) {
+  if (warp == LW) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- halo producer
       int as = 0; uint32_t aphase = 0;
@@ -258,9 +268,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             HDBG_T0();
             ptx::mbar_wait(a_empty(as), aphase ^ 1u);
             HDBG_ACC(0);
-            ptx::mbar_expect_tx(a_full(as), MT * G::BYTES);
+            ptx::mbar_expect_tx(a_full(as), (p.ablate & 8) ? 0 : MT * G::BYTES);
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
+              if (p.ablate & 8) break;
               if (GEO == 0)
                 ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
                                  cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
@@ -275,7 +286,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (p.dbg) { hd[1] = (unsigned long long)(clock64() - hd_start); hd[2] = (unsigned long long)(sup_end - sup_begin); }
       HDBG_FLUSH(0, 3);      // [0] A producer waits a_empty, [1] total, [2] super tiles
     }
-  } else if (warp == 13) {
+  } else if (warp == LW + 1) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- weight producer
       int ws = 0; uint32_t wphase = 0;
@@ -287,7 +298,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           for (int cb = 0; cb < seg.cblocks; ++cb) {
             for (int tap = 0; tap < seg.ntaps; ++tap) {
               ptx::mbar_wait(w_empty(ws), wphase ^ 1u);
-              ptx::mbar_expect_tx(w_full(ws), S::W_STAGE);
+              ptx::mbar_expect_tx(w_full(ws), (p.ablate & 4) ? 0 : S::W_STAGE);
+              if (!(p.ablate & 4))
               ptx::tma_load_2d(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws),
                                seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
               if (++ws == WST) { ws = 0; wphase ^= 1u; }
@@ -296,7 +308,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
-  } else if (warp == 15) {
+  } else if (warp == LW + 3) {
     // ------------------------------------------------------------------ MMA issuer
     // One elected thread runs the whole loop. A single thread retires dependent scalar instructions at
     // ~5 cycles each while an N=64 MMA occupies the tensor pipe for only 48 cycles, so the loop is kept
@@ -431,14 +443,17 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       ptx::mbar_arrive(tmem_empty(buf));
     }
     if (threadIdx.x == 128) HDBG_FLUSH(8, 1);
-  } else if (BLOCK_N != 16 && warp >= 4 && warp < 8) {
+  } else if (BLOCK_N != 16 && ((warp >= 4 && warp < 8) || (ESETS == 2 && warp >= 12 && warp < 16))) {
     // ------------------------------------------------------------------ epilogue
     constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
     constexpr int NSTG = S::NSTG;
     const int wq = warp & 3;
-    const int tid_e = threadIdx.x - 128;
-    const uint32_t slab_u32 = smem_base + S::STG_OFFSET + wq * (NSTG * 4096);
-    uint8_t* slab_gen = smem_gen + S::STG_OFFSET + wq * (NSTG * 4096);
+#define HALO_EPI_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(128 * ESETS) : "memory")
+    const int eset = warp >= 12 ? 1 : 0;                   // which epilogue set this warp belongs to
+    const int tid_e = (int)threadIdx.x - (eset ? 256 : 128);     // 0 .. 128*ESETS-1
+    const uint32_t slab_u32 = smem_base + S::STG_OFFSET + (eset * 4 + wq) * (NSTG * 4096);
+    uint8_t* slab_gen = smem_gen + S::STG_OFFSET + (eset * 4 + wq) * (NSTG * 4096);
+    int unit = 0;                                          // 64-channel units seen so far (same count in every set)
     const bool do_stats = p.stat_partial != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
@@ -469,6 +484,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N);
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
+          if (ESETS == 2 && ((unit++ & 1) != eset)) continue;      // the other set's unit
           const uint32_t sl = slab_u32 + (uint32_t)stg * 4096u;
           uint8_t* slg = slab_gen + stg * 4096;
           // the tensor store that last read this slab must have finished reading it
@@ -553,25 +569,26 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(acc[im][cc][1], acc[im][cc][3]);
               acc[im][cc][0] = acc[im][cc][1] = acc[im][cc][2] = acc[im][cc][3] = 0;
             }
-          epi_bar_sync();
-          for (int item = tid_e; item < IMGS * 2 * BLOCK_N; item += 128) {
+          HALO_EPI_SYNC();
+          for (int item = tid_e; item < IMGS * 2 * BLOCK_N; item += 128 * ESETS) {
             const int im = item / (2 * BLOCK_N), within = item - im * 2 * BLOCK_N;
             if (t0.b + im >= p.B) continue;            // odd batch: the pair's second image does not exist
             long long a = 0;
 #pragma unroll
-            for (int ww = 0; ww < 4; ++ww)
+            for (int ww = 0; ww < 4 * ESETS; ++ww)
               a += reinterpret_cast<const long long*>(smem_gen + S::STG_OFFSET + ww * (NSTG * 4096))[item];
             long long* dst = p.stat_partial + (((size_t)(t0.b + im) * p.stat_slots + slot) * p.Cout + n0) * 2 + within;
             *dst = a;
             if ((int)blockIdx.x == last_cta)
               for (int sl2 = slot + 1; sl2 < p.stat_slots; ++sl2) dst[(size_t)(sl2 - slot) * p.Cout * 2] = 0;
           }
-          epi_bar_sync();
+          HALO_EPI_SYNC();
         }
       }
     }
     if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
+#undef HALO_EPI_SYNC
   } else if (FUSE_GN && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
     // thread -> (16-byte channel chunk j, pixels p_first + 32 i): its 8 channels' (scale, shift) sit in
@@ -681,7 +698,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 14) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
+  if (warp == LW + 2) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
 }
 #endif  // __CUDACC__
 

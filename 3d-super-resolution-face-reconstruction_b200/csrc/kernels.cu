@@ -1,6 +1,10 @@
 // Non-GEMM kernels of the SR3 sampling step: GroupNorm(+Swish), head conv, tail conv fused with
 // the posterior update, mid-block attention core, nearest upsample, weight packing and the
 // noise-embedding bias table. HBM-bound kernels use 16-byte vector accesses on NHWC bf16.
+#include <mma.h>
+
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace b200sr3 {
@@ -306,6 +310,8 @@ __global__ void __launch_bounds__(HEAD_TW * HEAD_TH, 2)
 head_conv64_kernel(const float* __restrict__ cond, const float* __restrict__ x, int c_cond, int c_x,
                    const float* __restrict__ w_kc, const float* __restrict__ bias, int B, int R,
                    bf16* __restrict__ out, unsigned long long* __restrict__ stats) {
+  // Persistent: a CTA loads the [K][64] weights once and walks a contiguous run of tiles, so the
+  // statistics of an image leave the CTA as ONE set of 128 atomics per (CTA, image) instead of one per tile.
   constexpr int COUT = 64;
   extern __shared__ float hs[];
   const int Cin = c_cond + c_x;
@@ -316,65 +322,78 @@ head_conv64_kernel(const float* __restrict__ cond, const float* __restrict__ x, 
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
   const int tiles_x = R / HEAD_TW, tiles_y = R / HEAD_TH;
-  int tile = blockIdx.x;
-  const int x0 = (tile % tiles_x) * HEAD_TW; tile /= tiles_x;
-  const int y0 = (tile % tiles_y) * HEAD_TH;
-  const int b = tile / tiles_y;
+  const int total = B * tiles_x * tiles_y;
+  const int t_begin = (int)(((long long)blockIdx.x * total) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
 
   for (int i = tid; i < K * COUT / 4; i += blockDim.x)
     reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w_kc) + i);
   if (tid < 2 * COUT) sred[tid] = 0ull;
   constexpr int IW = HEAD_TW + 2, IH = HEAD_TH + 2;
-  for (int i = tid; i < Cin * IH * IW; i += blockDim.x) {
-    const int ix = i % IW, iy = (i / IW) % IH, ci = i / (IW * IH);
-    const int gx = x0 + ix - 1, gy = y0 + iy - 1;
-    float v = 0.f;
-    if (gx >= 0 && gx < R && gy >= 0 && gy < R)
-      v = (ci < c_cond) ? __ldg(cond + (((size_t)b * c_cond + ci) * R + gy) * R + gx)
-                        : __ldg(x + (((size_t)b * c_x + (ci - c_cond)) * R + gy) * R + gx);
-    in_s[i] = v;
-  }
-  __syncthreads();
+  int cur_b = -1;
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int x0 = (tile % tiles_x) * HEAD_TW;
+    const int y0 = ((tile / tiles_x) % tiles_y) * HEAD_TH;
+    const int b = tile / (tiles_x * tiles_y);
+    __syncthreads();                                // previous tile's reads of in_s (and sred flush) are done
+    if (stats && b != cur_b) {
+      if (cur_b >= 0 && tid < 2 * COUT) {
+        atomicAdd(stats + (size_t)cur_b * COUT * 2 + tid, sred[tid]);
+        sred[tid] = 0ull;
+      }
+      cur_b = b;
+    }
+    for (int i = tid; i < Cin * IH * IW; i += blockDim.x) {
+      const int ix = i % IW, iy = (i / IW) % IH, ci = i / (IW * IH);
+      const int gx = x0 + ix - 1, gy = y0 + iy - 1;
+      float v = 0.f;
+      if (gx >= 0 && gx < R && gy >= 0 && gy < R)
+        v = (ci < c_cond) ? __ldg(cond + (((size_t)b * c_cond + ci) * R + gy) * R + gx)
+                          : __ldg(x + (((size_t)b * c_x + (ci - c_cond)) * R + gy) * R + gx);
+      in_s[i] = v;
+    }
+    __syncthreads();
 
-  float acc[COUT];
+    float acc[COUT];
 #pragma unroll
-  for (int j = 0; j < COUT; j += 4) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
-    acc[j] = bv.x; acc[j + 1] = bv.y; acc[j + 2] = bv.z; acc[j + 3] = bv.w;
-  }
-  for (int tap = 0; tap < 9; ++tap) {
-    const int ky = tap / 3, kx = tap % 3;
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float v = in_s[(ci * IH + ty + ky) * IW + tx + kx];
-      const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * Cin + ci) * COUT);
+    for (int j = 0; j < COUT; j += 4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
+      acc[j] = bv.x; acc[j + 1] = bv.y; acc[j + 2] = bv.z; acc[j + 3] = bv.w;
+    }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float v = in_s[(ci * IH + ty + ky) * IW + tx + kx];
+        const float4* wr = reinterpret_cast<const float4*>(w_s + (tap * Cin + ci) * COUT);
 #pragma unroll
-      for (int j = 0; j < COUT / 4; ++j) {
-        const float4 w = wr[j];
-        acc[4 * j] = fmaf(v, w.x, acc[4 * j]);
-        acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        for (int j = 0; j < COUT / 4; ++j) {
+          const float4 w = wr[j];
+          acc[4 * j] = fmaf(v, w.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+    bf16* dst = out + (((size_t)b * R + y0 + ty) * R + x0 + tx) * COUT;
+#pragma unroll
+    for (int j = 0; j < COUT; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(acc + j);
+
+    if (stats) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float f[32], q[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { f[j] = acc[half * 32 + j]; q[j] = f[j] * f[j]; }
+        const float s_sum = warp_transpose_sum32(f, tx);
+        const float s_sq = warp_transpose_sum32(q, tx);
+        atomicAdd(&sred[(half * 32 + tx) * 2], (unsigned long long)__float2ll_rn(s_sum * STAT_FIXED_SCALE));
+        atomicAdd(&sred[(half * 32 + tx) * 2 + 1], (unsigned long long)__float2ll_rn(s_sq * STAT_FIXED_SCALE));
       }
     }
   }
-  bf16* dst = out + (((size_t)b * R + y0 + ty) * R + x0 + tx) * COUT;
-#pragma unroll
-  for (int j = 0; j < COUT; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(acc + j);
-
-  if (stats) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float f[32], q[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { f[j] = acc[half * 32 + j]; q[j] = f[j] * f[j]; }
-      const float s_sum = warp_transpose_sum32(f, tx);
-      const float s_sq = warp_transpose_sum32(q, tx);
-      atomicAdd(&sred[(half * 32 + tx) * 2], (unsigned long long)__float2ll_rn(s_sum * STAT_FIXED_SCALE));
-      atomicAdd(&sred[(half * 32 + tx) * 2 + 1], (unsigned long long)__float2ll_rn(s_sq * STAT_FIXED_SCALE));
-    }
-    __syncthreads();
-    if (tid < 2 * COUT) atomicAdd(stats + (size_t)b * COUT * 2 + tid, sred[tid]);
-  }
+  __syncthreads();
+  if (stats && cur_b >= 0 && tid < 2 * COUT) atomicAdd(stats + (size_t)cur_b * COUT * 2 + tid, sred[tid]);
 }
 
 bool head_conv_fast_path(int c_in, int R, int Cout) {
@@ -388,7 +407,11 @@ void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, co
     const int cin = c_cond + c_x;
     const size_t smem = (size_t)(cin * 9 * 64 + cin * (HEAD_TH + 2) * (HEAD_TW + 2)) * sizeof(float);
     if (stats) CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * 64 * 2 * sizeof(long long), s));
-    const unsigned blocks = (unsigned)(B * (R / HEAD_TH) * (R / HEAD_TW));
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned tiles = (unsigned)(B * (R / HEAD_TH) * (R / HEAD_TW));
+    const unsigned blocks = std::min<unsigned>(tiles, (unsigned)(2 * sms));
     head_conv64_kernel<<<blocks, HEAD_TW * HEAD_TH, smem, s>>>(cond, x, c_cond, c_x, w_kc, bias, B, R, out,
                                                               reinterpret_cast<unsigned long long*>(stats));
     CUDA_CHECK(cudaGetLastError());
@@ -710,8 +733,106 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* _
   }
 }
 
+// Tensor-core version for HW in {16, 32, 48, 64} tokens: a CTA owns 16 queries of one image. Q (16 rows)
+// and K (all tokens) are staged in shared memory with coalesced 16-byte loads (rows padded by 8
+// elements against bank conflicts), S = Q K^T runs on mma.sync (bf16 in, fp32 out: a 0.01%-of-FLOPs
+// op, the legacy tensor path is plenty), the softmax is fp32, P is rounded to bf16 and O = P V reuses
+// K's buffer for V.
+__global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                            int HW, int C) {
+  using namespace nvcuda;
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int ld = C + 8;                                        // padded row length (elements)
+  bf16* q_s = reinterpret_cast<bf16*>(att_smem);               // [16][ld]
+  bf16* kv_s = q_s + 16 * ld;                                  // [HW][ld]
+  float* s_s = reinterpret_cast<float*>(kv_s + (size_t)HW * ld);   // [16][HW]
+  bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * HW);          // [16][HW]
+  float* scr = reinterpret_cast<float*>(p_s + 16 * HW);        // [4][256]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, q0 = blockIdx.x * 16;
+  const size_t row = (size_t)3 * C;
+  const bf16* base = qkv + (size_t)b * HW * row;
+  const int cv = C >> 3;
+  for (int i = tid; i < 16 * cv; i += 128) {
+    const int r = i / cv, c = i - r * cv;
+    *reinterpret_cast<uint4*>(q_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(q0 + r) * row + c * 8));
+  }
+  for (int i = tid; i < HW * cv; i += 128) {
+    const int r = i / cv, c = i - r * cv;
+    *reinterpret_cast<uint4*>(kv_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * row + C + c * 8));
+  }
+  __syncthreads();
+  // ---- S = Q K^T: one 16x16 tile of keys per warp pass
+  for (int t = warp; t < HW / 16; t += 4) {
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+    wmma::fill_fragment(acc, 0.f);
+    for (int k = 0; k < C; k += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> a;
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> kb;
+      wmma::load_matrix_sync(a, q_s + k, ld);
+      wmma::load_matrix_sync(kb, kv_s + (size_t)t * 16 * ld + k, ld);
+      wmma::mma_sync(acc, a, kb, acc);
+    }
+    wmma::store_matrix_sync(s_s + t * 16, acc, HW, wmma::mem_row_major);
+  }
+  __syncthreads();
+  // ---- V replaces K while the softmax runs
+  for (int i = tid; i < HW * cv; i += 128) {
+    const int r = i / cv, c = i - r * cv;
+    *reinterpret_cast<uint4*>(kv_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * row + 2 * C + c * 8));
+  }
+  {
+    // 8 lanes per query row (unet.py:133-135: scores / sqrt(C), softmax over all keys)
+    const int r = tid >> 3, sub = tid & 7;
+    const float scale = rsqrtf((float)C);
+    float v[8];
+    float mx = -INFINITY;
+    int n = 0;
+    for (int j = sub; j < HW; j += 8) { v[n] = s_s[r * HW + j] * scale; mx = fmaxf(mx, v[n]); ++n; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = 0; i < n; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    n = 0;
+    for (int j = sub; j < HW; j += 8) p_s[r * HW + j] = __float2bfloat16_rn(v[n++] * inv);
+  }
+  __syncthreads();
+  // ---- O = P V: 16-channel tiles round-robin over the warps
+  float* my = scr + warp * 256;
+  for (int t = warp; t < C / 16; t += 4) {
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+    wmma::fill_fragment(acc, 0.f);
+    for (int k = 0; k < HW; k += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> a;
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> vb;
+      wmma::load_matrix_sync(a, p_s + k, HW);
+      wmma::load_matrix_sync(vb, kv_s + (size_t)k * ld + t * 16, ld);
+      wmma::mma_sync(acc, a, vb, acc);
+    }
+    wmma::store_matrix_sync(my, acc, 16, wmma::mem_row_major);
+    __syncwarp();
+    const int r = lane >> 1, h = lane & 1;
+    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + q0 + r) * C + t * 16 + h * 8) = pack8(my + r * 16 + h * 8);
+    __syncwarp();
+  }
+}
+
 void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStream_t s) {
   REQUIRE(C % 8 == 0 && C <= 1024, "attention: C must be a multiple of 8 and <= 1024");
+  if (HW % 16 == 0 && HW <= 64 && C % 16 == 0) {
+    const size_t smem = (size_t)(16 + HW) * (C + 8) * 2 + (size_t)16 * HW * 4 + (size_t)16 * HW * 2 + 4 * 256 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    attention_mma_kernel<<<dim3(HW / 16, B), 128, smem, s>>>(qkv, out, HW, C);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   const size_t smem = (size_t)ATT_WARPS * HW * sizeof(float);
   REQUIRE(smem <= 160 * 1024, "attention: too many tokens");
   if (smem > 48 * 1024)
