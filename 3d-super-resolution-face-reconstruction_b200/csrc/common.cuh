@@ -47,6 +47,28 @@ struct StepCtl {
   long long numel;     // B*3*R*R, stride between entries of the injected list
 };
 
+// ------------------------------------------------------------------------------- launches
+// Every kernel of the per-step chain can be launched with programmatic dependent launch (PDL,
+// B200SR3_PDL=1): kernel N+1 may be scheduled while kernel N drains, runs its prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) and blocks in pdl_wait() until N has completed and flushed.
+// Each of those kernels calls pdl_launch_dependents() and, before it touches global memory,
+// pdl_wait(); without the launch attribute both are no-ops. Off by default: see pdl_enabled().
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // ------------------------------------------------------------------------------- small helpers
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -64,6 +86,9 @@ struct Act {  // NHWC bf16 activation
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (both ~2^-22 relative: far below the bf16
 // rounding of the stored result); the IEEE division this replaces cost ~15 instructions.
 __device__ __forceinline__ float swish_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }

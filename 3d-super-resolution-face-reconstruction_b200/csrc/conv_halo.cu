@@ -35,9 +35,8 @@ void conv_halo_init_device() {
 
 template <int BN, int MT, int GEO = 0>
 static void launch_halo(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
-  if (gn) conv_halo_kernel<BN, MT, true, GEO><<<grid, halo_threads(BN), HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
-  else conv_halo_kernel<BN, MT, false, GEO><<<grid, halo_threads(BN), HaloSmem<BN, MT, GEO>::TOTAL, s>>>(p);
-  CUDA_CHECK(cudaGetLastError());
+  if (gn) launch_pdl(conv_halo_kernel<BN, MT, true, GEO>, dim3(grid), dim3(halo_threads(BN)), HaloSmem<BN, MT, GEO>::TOTAL, s, p);
+  else launch_pdl(conv_halo_kernel<BN, MT, false, GEO>, dim3(grid), dim3(halo_threads(BN)), HaloSmem<BN, MT, GEO>::TOTAL, s, p);
 }
 
 static bool geo1(int H, int W) { return H == 8 && W == 8; }   // two whole 8x8 images per tile

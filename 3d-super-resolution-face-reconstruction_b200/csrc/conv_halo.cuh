@@ -49,7 +49,9 @@ constexpr int HALO_STRIDE = 23552;                       // rounded up to the 10
 // + staging = ~370 KB per tile at 128 B/clk), not by epilogue issue slots - so every shape runs one set.
 constexpr int halo_esets(int block_n) { return (void)block_n, 1; }
 constexpr int halo_threads(int block_n) { return 512 + 128 * (halo_esets(block_n) - 1); }
-constexpr int HALO_A_STAGES = 3;
+// halo ring depth: 3 (load / transform / MMA). A 6-deep ring for one-tile BLOCK_N = 64 shapes was tried for
+// the single-tap shortcut segments and does not pay: those layers are shared-memory-bandwidth bound.
+constexpr int halo_a_stages(int block_n, int mt, int geo) { return (void)block_n, (void)mt, (void)geo, 3; }
 constexpr int HALO_MAX_SEGS = 4;
 
 // Tile geometry. GEO 0: an 8 x 16 pixel tile of one image, halo 10 x 18. GEO 1 (8 x 8 images): a tile is
@@ -114,7 +116,8 @@ struct alignas(64) ConvHaloParams {
 template <int BLOCK_N, int MT, int GEO = 0>
 struct HaloSmem {
   static constexpr int A_STAGE = MT * HaloGeo<GEO>::STRIDE;
-  static constexpr int A_BYTES = HALO_A_STAGES * A_STAGE;
+  static constexpr int AST = halo_a_stages(BLOCK_N, MT, GEO);
+  static constexpr int A_BYTES = AST * A_STAGE;
   static constexpr int W_STAGE = BLOCK_N * 128;
   static constexpr int NSTG = (BLOCK_N == 256 || MT == 2) ? 1 : 2;   // staging slabs per epilogue warp
   static constexpr int ESETS = halo_esets(BLOCK_N);
@@ -188,7 +191,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   // warp groups: 0 = transform A, 1 = epilogue A, 2 = transform B, [3 = epilogue B], last = single-thread roles
   constexpr int LW = 4 * (2 + ESETS);        // first warp of the last group: LW+0 halo producer, +1 weight producer,
                                               // +2 TMEM allocator, +3 MMA issuer
-  constexpr int AST = HALO_A_STAGES, WST = S::W_STAGES;
+  constexpr int AST = S::AST, WST = S::W_STAGES;
   constexpr int NBUF = 2;
   static_assert(NBUF * MT * BLOCK_N <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
@@ -234,6 +237,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();            // everything above overlapped the previous kernel's tail; its results are needed from here
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -376,6 +380,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
         ptx::umma_commit(tmem_full(buf));
       }
+      // all of this CTA's MMAs are issued: only the last epilogue remains, let the next kernel's CTAs
+      // be scheduled (they run their prologue and block in pdl_wait until this grid has completed)
+      pdl_launch_dependents();
       HDBG_FLUSH(4, 3);      // [4] MMA waits A ready, [5] waits W full, [6] waits TMEM empty
     }
   } else if (BLOCK_N == 16 && warp >= 4 && warp < 8) {

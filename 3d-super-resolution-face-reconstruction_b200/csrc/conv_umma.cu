@@ -65,8 +65,7 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <int BN, int ST, int MW>
 static void launch_conv(const ConvParams& p, int grid, cudaStream_t s) {
-  conv_umma_kernel<BN, ST, MW><<<grid, CONV_THREADS, ConvSmem<BN, ST>::TOTAL, s>>>(p);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(conv_umma_kernel<BN, ST, MW>, dim3(grid), dim3(CONV_THREADS), ConvSmem<BN, ST>::TOTAL, s, p);
 }
 
 // smem ring depth per BLOCK_N: 192 KB of stages in every case

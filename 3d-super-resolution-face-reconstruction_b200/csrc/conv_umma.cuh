@@ -301,10 +301,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     }
     ptx::fence_barrier_init();
   }
+  pdl_launch_dependents();
   if (warp == 3) ptx::tmem_alloc(tmem_slot, NBUF * BLOCK_N);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 

@@ -9,6 +9,13 @@
 
 namespace b200sr3 {
 
+// Measured on B200 (bench.py, T=600, B=32): 3.60 ms per sampling step plain, 3.63 ms with PDL edges in the
+// graph - graph replay already starts a node within ~1 us of its predecessor - so PDL is opt-in.
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B200SR3_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+
 // =============================================================================== GroupNorm
 // Statistics arrive as per-(image, channel) (sum, sumsq) pairs "chansum[b][c][2]", produced in the
 // epilogue of the conv that wrote the tensor (conv_umma.cuh) or, for tensors no tensor-core conv
@@ -25,6 +32,8 @@ constexpr int GN_THREADS = 384;
 // Per-CTA partial (sum, sumsq) per channel; the last CTA of an image (ticket) reduces the
 // partials in a fixed order (deterministic) into chansum.
 __global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[GN_THREADS * 16];
   __shared__ int is_last;
   const int C = g.C;
@@ -93,6 +102,8 @@ __global__ void __launch_bounds__(GN_THREADS) chan_stats_kernel(ChanStatsPlan g)
 // y = [swish]((x - mean_g) * rstd_g * gamma + beta) over [src0 | src1]; grid (apply_chunks, B):
 // a CTA forms the group statistics of its image from chansum, then streams a pixel range.
 __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(GnPlan g, int apply_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float chan[1024 * 2];
   __shared__ float gstat[64 * 2];
   const int C = g.C0 + g.C1;
@@ -168,6 +179,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(GnPlan g, int a
 
 // Same statistics code as gn_apply_kernel's preamble, for the fused path: one CTA per image.
 __global__ void __launch_bounds__(256) gn_scale_shift_kernel(GnPlan g, float2* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float chan[1024 * 2];
   __shared__ float gstat[64 * 2];
   const int C = g.C0 + g.C1;
@@ -210,7 +223,7 @@ void launch_gn_scale_shift(const GnPlan& g, float2* out, cudaStream_t s) {
   const int C = g.C0 + g.C1;
   REQUIRE(C <= 1024 && C % g.groups == 0 && g.groups <= 64, "GroupNorm: unsupported channel count");
   REQUIRE(g.stats0 && (g.C1 == 0 || g.stats1), "GroupNorm: missing channel statistics");
-  gn_scale_shift_kernel<<<g.B, 256, 0, s>>>(g, out);
+  launch_pdl(gn_scale_shift_kernel, dim3(g.B), dim3(256), 0, s, g, out);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -225,7 +238,7 @@ int chan_stats_chunks(int HW, int C) {
 
 void launch_chan_stats(const ChanStatsPlan& g, cudaStream_t s) {
   REQUIRE(g.C % 8 == 0 && g.C <= 1024 && GN_THREADS % (g.C / 8) == 0, "chan_stats: unsupported channel count");
-  chan_stats_kernel<<<dim3(g.chunks, g.B), GN_THREADS, 0, s>>>(g);
+  launch_pdl(chan_stats_kernel, dim3(g.chunks, g.B), dim3(GN_THREADS), 0, s, g);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -239,7 +252,7 @@ void launch_gn_apply(const GnPlan& g, cudaStream_t s) {
   if (ch < 1) ch = 1;
   if (ch > g.HW) ch = g.HW;
   if (ch > 1024) ch = 1024;
-  gn_apply_kernel<<<dim3((int)ch, g.B), GN_THREADS, 0, s>>>(g, (int)ch);
+  launch_pdl(gn_apply_kernel, dim3((int)ch, g.B), dim3(GN_THREADS), 0, s, g, (int)ch);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -251,6 +264,8 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ w_kc,
                                                         const float* __restrict__ bias, int B, int R,
                                                         int Cout, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float w_s[];   // [K][Cout]
   const int Cin = c_cond + c_x;
   const int K = Cin * 9;
@@ -310,6 +325,8 @@ __global__ void __launch_bounds__(HEAD_TW * HEAD_TH, 2)
 head_conv64_kernel(const float* __restrict__ cond, const float* __restrict__ x, int c_cond, int c_x,
                    const float* __restrict__ w_kc, const float* __restrict__ bias, int B, int R,
                    bf16* __restrict__ out, unsigned long long* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   // Persistent: a CTA loads the [K][64] weights once and walks a contiguous run of tiles, so the
   // statistics of an image leave the CTA as ONE set of 128 atomics per (CTA, image) instead of one per tile.
   constexpr int COUT = 64;
@@ -412,8 +429,8 @@ void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, co
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned tiles = (unsigned)(B * (R / HEAD_TH) * (R / HEAD_TW));
     const unsigned blocks = std::min<unsigned>(tiles, (unsigned)(2 * sms));
-    head_conv64_kernel<<<blocks, HEAD_TW * HEAD_TH, smem, s>>>(cond, x, c_cond, c_x, w_kc, bias, B, R, out,
-                                                              reinterpret_cast<unsigned long long*>(stats));
+    launch_pdl(head_conv64_kernel, dim3(blocks), dim3(HEAD_TW * HEAD_TH), smem, s, cond, x, c_cond, c_x, w_kc, bias, B, R,
+               out, reinterpret_cast<unsigned long long*>(stats));
     CUDA_CHECK(cudaGetLastError());
     return;
   }
@@ -425,8 +442,8 @@ void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, co
   const long long npix = (long long)B * R * R;
   const size_t smem = (size_t)(c_cond + c_x) * 9 * Cout * sizeof(float);
   REQUIRE(smem <= 48 * 1024, "head conv: weights exceed 48 KB of shared memory");
-  head_conv_kernel<<<(unsigned)((npix + ppb - 1) / ppb), threads, smem, s>>>(cond, x, c_cond, c_x, w_kc, bias,
-                                                                            B, R, Cout, out);
+  launch_pdl(head_conv_kernel, dim3((unsigned)((npix + ppb - 1) / ppb)), dim3(threads), smem, s, cond, x, c_cond, c_x,
+             w_kc, bias, B, R, Cout, out);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -437,6 +454,8 @@ void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, co
 // then the reference's update, op for op (diffusion.py:150-151, 175-176, 159-160, 186-187).
 template <int OC>
 __global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float w_s[];   // [OC][9][C]
   const int C = t.C, R = t.R;
   for (int i = threadIdx.x; i < OC * 9 * C; i += blockDim.x) w_s[i] = t.w[i];
@@ -512,6 +531,8 @@ __global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
 // combined with xor-shuffles and lane o < OC of the group applies the posterior update of channel o.
 template <int OC>
 __global__ void __launch_bounds__(256) tail_split_kernel(TailPlan t) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float w_s[];   // [OC][9][C]
   const int C = t.C, R = t.R;
   for (int i = threadIdx.x; i < OC * 9 * C; i += blockDim.x) w_s[i] = t.w[i];
@@ -591,9 +612,9 @@ void launch_tail(const TailPlan& t, cudaStream_t s) {
     const int ppb = 256 / lpp;
     const unsigned blocks = (unsigned)((npix + ppb - 1) / ppb);
     switch (t.OC) {
-      case 1: tail_split_kernel<1><<<blocks, 256, smem, s>>>(t); break;
-      case 3: tail_split_kernel<3><<<blocks, 256, smem, s>>>(t); break;
-      case 4: tail_split_kernel<4><<<blocks, 256, smem, s>>>(t); break;
+      case 1: launch_pdl(tail_split_kernel<1>, dim3(blocks), dim3(256), smem, s, t); break;
+      case 3: launch_pdl(tail_split_kernel<3>, dim3(blocks), dim3(256), smem, s, t); break;
+      case 4: launch_pdl(tail_split_kernel<4>, dim3(blocks), dim3(256), smem, s, t); break;
       default: throw Error("tail conv: out_channel must be 1, 3 or 4");
     }
     CUDA_CHECK(cudaGetLastError());
@@ -601,9 +622,9 @@ void launch_tail(const TailPlan& t, cudaStream_t s) {
   }
   const unsigned blocks = (unsigned)((npix + 127) / 128);
   switch (t.OC) {
-    case 1: tail_kernel<1><<<blocks, 128, smem, s>>>(t); break;
-    case 3: tail_kernel<3><<<blocks, 128, smem, s>>>(t); break;
-    case 4: tail_kernel<4><<<blocks, 128, smem, s>>>(t); break;
+    case 1: launch_pdl(tail_kernel<1>, dim3(blocks), dim3(128), smem, s, t); break;
+    case 3: launch_pdl(tail_kernel<3>, dim3(blocks), dim3(128), smem, s, t); break;
+    case 4: launch_pdl(tail_kernel<4>, dim3(blocks), dim3(128), smem, s, t); break;
     default: throw Error("tail conv: out_channel must be 1, 3 or 4");
   }
   CUDA_CHECK(cudaGetLastError());
@@ -631,9 +652,13 @@ void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, 
   CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void ctl_advance_kernel(StepCtl* ctl) { ctl->t -= 1; }
+__global__ void ctl_advance_kernel(StepCtl* ctl) {
+  pdl_launch_dependents();
+  pdl_wait();
+  ctl->t -= 1;
+}
 void launch_ctl_advance(StepCtl* ctl, cudaStream_t s) {
-  ctl_advance_kernel<<<1, 1, 0, s>>>(ctl);
+  launch_pdl(ctl_advance_kernel, dim3(1), dim3(1), 0, s, ctl);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -658,6 +683,8 @@ constexpr int ATT_WARPS = 8;
 constexpr int ATT_MAXV = 4;   // C <= 1024
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* __restrict__ qkv,
                                                                    bf16* __restrict__ out, int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sc_s[];   // [ATT_WARPS][HW]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -740,6 +767,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* _
 // K's buffer for V.
 __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                             int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   using namespace nvcuda;
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int ld = C + 8;                                        // padded row length (elements)
@@ -829,7 +858,7 @@ void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStre
       CUDA_CHECK(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    attention_mma_kernel<<<dim3(HW / 16, B), 128, smem, s>>>(qkv, out, HW, C);
+    launch_pdl(attention_mma_kernel, dim3(HW / 16, B), dim3(128), smem, s, qkv, out, HW, C);
     CUDA_CHECK(cudaGetLastError());
     return;
   }
@@ -837,7 +866,7 @@ void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStre
   REQUIRE(smem <= 160 * 1024, "attention: too many tokens");
   if (smem > 48 * 1024)
     CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_kernel<<<dim3(ceil_div(HW, ATT_WARPS), B), ATT_WARPS * 32, smem, s>>>(qkv, out, HW, C);
+  launch_pdl(attention_kernel, dim3(ceil_div(HW, ATT_WARPS), B), dim3(ATT_WARPS * 32), smem, s, qkv, out, HW, C);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -242,13 +242,14 @@ def main():
     gn_ms, gn_bytes = sum(m for m, _ in gn), sum(b for _, b in gn)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (all tcgen05 conv launches of one sampling step)",
+    roofline = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_umma_kernel (all tcgen05 conv launches of one sampling step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a long step)",
                 "launches_per_step": len(conv), "flops_per_step": conv_flops, "conv_ms_per_step": conv_ms,
                 "conv_share_of_step": conv_ms / step_ms,
                 "whole_step_frac": value / world * T * GFLOP_PER_IMG_STEP[R] * 1e9 / (peak * 1e12)}
-    roofline_hbm = {"bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel", "achieved": gn_bytes / (gn_ms * 1e-3) / 1e9,
+    roofline_hbm = {"bound": "hbm", "kernel": "gn_apply_kernel (the GroupNorm passes that are not fused into a conv)",
+                    "achieved": gn_bytes / (gn_ms * 1e-3) / 1e9,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "ms_per_step": gn_ms, "share_of_step": gn_ms / step_ms, "traffic": None}
     line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps,
