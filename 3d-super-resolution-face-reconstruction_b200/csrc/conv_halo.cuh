@@ -122,7 +122,9 @@ struct HaloSmem {
   static constexpr int NSTG = (BLOCK_N == 256 || MT == 2) ? 1 : 2;   // staging slabs per epilogue warp
   static constexpr int ESETS = halo_esets(BLOCK_N);
   static constexpr int STG_BYTES = 4 * ESETS * NSTG * 4096;
-  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 8;  // (scale, shift) of the current image (pair), <= 1024 channels
+  // (scale, shift) of the current image (pair), <= 1024 channels; every 8-channel group is followed by
+  // 16 bytes of padding so that the eight groups a warp reads at once fall into different banks
+  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
   static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
@@ -607,7 +609,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int j = tt & 7;
     const int p_first = tt >> 3;
     const bool do_swish = p.gn_swish != 0;
-    float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C], halved if swish
+    float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C (padded)], halved if swish
+    const int gn_pitch = p.gn_C + 2 * (p.gn_C >> 3);
     int tab_b = -1;
     int as = 0; uint32_t aphase = 0;
     HDBG_DECL();
@@ -622,7 +625,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           const int c = idx - im * p.gn_C;
           float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
           if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
-          gtab[idx] = v;
+          gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;       // 10 float2 slots per 8 channels
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
         tab_b = t[0].b;
@@ -635,7 +638,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           if (seg.gn_off >= 0) {
 #pragma unroll
             for (int im = 0; im < IMGS; ++im) {
-              const float4* g4 = reinterpret_cast<const float4*>(gtab + im * p.gn_C + seg.gn_off + cb * CONV_BLOCK_K + j * 8);
+              const int c0 = seg.gn_off + cb * CONV_BLOCK_K + j * 8;
+              const float4* g4 = reinterpret_cast<const float4*>(gtab + im * gn_pitch + c0 + 2 * (c0 >> 3));
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 v = g4[i];

@@ -277,6 +277,12 @@ void Engine::finalize_weights(cudaStream_t s) {
       case LayerKind::HeadConv: {
         head_w_ = (float*)dalloc((size_t)l.cout * l.c_x * 9 * sizeof(float));
         launch_pack_head_weight(T_(l.name + ".weight"), head_w_, l.cout, l.c_x, s);
+        head_pc_ = PackedConv();
+        if ((l.c_x == 2 || l.c_x == 6 || l.c_x == 8) && l.cout % 64 == 0) {
+          head_pc_.cout = l.cout; head_pc_.taps = 9; head_pc_.cin_main = CONV_BLOCK_K; head_pc_.k_total = 9 * CONV_BLOCK_K;
+          head_pc_.w = (bf16*)dalloc((size_t)l.cout * head_pc_.k_total * sizeof(bf16));
+          launch_pack_head_split_weight(T_(l.name + ".weight"), head_pc_.w, l.cout, l.c_x, s);
+        }
         break;
       }
       case LayerKind::Down: {
@@ -525,6 +531,21 @@ void Engine::build_workspace(Workspace& ws) {
   for (const LayerDesc& l : layers_) {
     switch (l.kind) {
       case LayerKind::HeadConv: {
+        if (use_halo_ && head_pc_.w && conv_halo_eligible(R, R, 1, l.cout)) {
+          // downs.0 on the tensor cores: split-precision operand (x_t is never rounded), then a halo conv
+          Act hp = act(R, R, CONV_BLOCK_K);
+          const float* cond = cfg_.conditional ? ws.cond : nullptr;
+          const int cc = cfg_.conditional ? oc : 0;
+          const float* xw = ws.x;
+          bf16* hdst = hp.ptr;
+          ws.ops.push_back(Op{l.name + ".pack", false, [=](cudaStream_t s) {
+            launch_head_pack(cond, xw, cc, oc, B, R, hdst, s);
+          }});
+          cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, nullptr, 0, true);
+          ws.ops.back().flops = 2.0 * B * R * R * (double)l.cout * 9.0 * l.c_x;      // reference graph: K = 9 * in_channel
+          feats.push_back(cur);
+          break;
+        }
         cur = act(R, R, l.cout);
         const float* cond = cfg_.conditional ? ws.cond : nullptr;
         const int cc = cfg_.conditional ? oc : 0;

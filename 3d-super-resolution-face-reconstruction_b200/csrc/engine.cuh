@@ -128,6 +128,7 @@ class Engine {
   int noise_total_ = 0;
   float *head_w_ = nullptr, *tail_w_ = nullptr;
   PackedConv tail_pc_;        // final_conv as a 16-row bf16 GEMM operand (halo conv tail)
+  PackedConv head_pc_;        // downs.0 as a split-precision bf16 GEMM operand (halo conv head)
   float *wall_ = nullptr, *ball_ = nullptr;
   std::vector<void*> owned_;
 

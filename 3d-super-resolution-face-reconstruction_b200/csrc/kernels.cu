@@ -413,6 +413,71 @@ head_conv64_kernel(const float* __restrict__ cond, const float* __restrict__ x, 
   if (stats && cur_b >= 0 && tid < 2 * COUT) atomicAdd(stats + (size_t)cur_b * COUT * 2 + tid, sred[tid]);
 }
 
+// ---- head conv on the tensor cores: operand preparation
+// The 6 -> 64 head conv must not round x_t to bf16 (the sampler state is fp32 all the way), so the
+// tensor-core version feeds a SPLIT operand: channels [0,n) hold hi = bf16(v), [n,2n) hold lo = bf16(v - hi)
+// and [2n,3n) hold hi again; the packed weights carry (w_hi, w_hi, w_lo) in those positions, so the GEMM
+// forms w_hi*v_hi + w_hi*v_lo + w_lo*v_hi = w*v up to 2^-16 relative, accumulated in fp32.
+template <int N>
+__global__ void __launch_bounds__(256) head_pack_kernel(const float* __restrict__ cond, const float* __restrict__ x,
+                                                        int c_cond, int B, int R, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long npix = (long long)B * R * R;
+  const size_t plane = (size_t)R * R;
+  const int c_x = N - c_cond;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(pix / (long long)plane);
+    const size_t off = (size_t)(pix - (long long)b * (long long)plane);
+    float row[32];                                  // 3N <= 24 used values, fully unrolled -> registers
+#pragma unroll
+    for (int i = 0; i < 32; ++i) row[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      const float v = (c < c_cond) ? __ldg(cond + ((size_t)b * c_cond + c) * plane + off)
+                                   : __ldg(x + ((size_t)b * c_x + (c - c_cond)) * plane + off);
+      const float hi = __bfloat162float(__float2bfloat16_rn(v));
+      row[c] = hi;
+      row[N + c] = v - hi;
+      row[2 * N + c] = hi;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * 64);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = pack8(row + 8 * i);
+#pragma unroll
+    for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+void launch_head_pack(const float* cond, const float* x, int c_cond, int c_x, int B, int R, bf16* out, cudaStream_t s) {
+  const int n = c_cond + c_x;
+  REQUIRE(n == 2 || n == 6 || n == 8, "head pack: in_channel must be 2, 6 or 8");
+  const long long npix = (long long)B * R * R;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (n == 6) launch_pdl(head_pack_kernel<6>, dim3((unsigned)blocks), dim3(256), 0, s, cond, x, c_cond, B, R, out);
+  else if (n == 2) launch_pdl(head_pack_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, s, cond, x, c_cond, B, R, out);
+  else launch_pdl(head_pack_kernel<8>, dim3((unsigned)blocks), dim3(256), 0, s, cond, x, c_cond, B, R, out);
+}
+// OIHW fp32 [Cout][n][3][3] -> [Cout][9*64] bf16 in the split layout above
+__global__ void pack_head_split_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int n) {
+  const int total = Cout * 9 * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % 64, tap = (idx / 64) % 9, o = idx / (64 * 9);
+    float v = 0.f;
+    if (c < 3 * n) {
+      const float w = src[((size_t)o * n + (c % n)) * 9 + tap];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      v = (c < 2 * n) ? hi : (w - hi);
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+void launch_pack_head_split_weight(const float* src, bf16* dst, int Cout, int n, cudaStream_t s) {
+  pack_head_split_weight_kernel<<<(Cout * 9 * 64 + 255) / 256, 256, 0, s>>>(src, dst, Cout, n);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 bool head_conv_fast_path(int c_in, int R, int Cout) {
   return Cout == 64 && R % HEAD_TW == 0 && R % HEAD_TH == 0 &&
          (size_t)(c_in * 9 * 64 + c_in * (HEAD_TH + 2) * (HEAD_TW + 2)) * sizeof(float) <= 48 * 1024;

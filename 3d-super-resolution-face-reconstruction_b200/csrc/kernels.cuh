@@ -46,6 +46,11 @@ bool head_conv_fast_path(int c_in, int R, int Cout);
 void launch_head_conv(const float* cond, const float* x, int c_cond, int c_x, const float* w_kc,
                       const float* bias, int B, int R, int Cout, bf16* out, long long* stats, cudaStream_t s);
 
+// Tensor-core head conv: split (hi, lo, hi) bf16 operand [B,R,R,64] from the fp32 NCHW inputs and the matching
+// (w_hi, w_hi, w_lo) weight packing [Cout][9*64]; the conv itself is a halo conv (conv_halo.cuh).
+void launch_head_pack(const float* cond, const float* x, int c_cond, int c_x, int B, int R, bf16* out, cudaStream_t s);
+void launch_pack_head_split_weight(const float* src, bf16* dst, int Cout, int n, cudaStream_t s);
+
 // ---- tail (unet.py:233 final conv on the normalised tensor) fused with the posterior update
 // (diffusion.py:144-187): eps = conv3x3(src) ; x0 = clamp(A x - B eps) ; x' = c1 x0 + c2 x + sigma z
 struct TailPlan {
