@@ -177,34 +177,41 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(GnPlan g, int a
   for (; p < p_end; p += rows) emit(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * cs)), p);
 }
 
-// Same statistics code as gn_apply_kernel's preamble, for the fused path: one CTA per image.
-__global__ void __launch_bounds__(256) gn_scale_shift_kernel(GnPlan g, float2* __restrict__ out) {
+// Same statistics as gn_apply_kernel's preamble, for the fused path: one CTA per image. The kernel is pure
+// latency (it sits between two convs 57 times per step), so every (slot, channel) partial is fetched by its
+// own thread - one L2 round trip instead of `slots` dependent ones - and summed with shared-memory int64
+// atomics (integer addition: the order does not matter, the result is exact and deterministic).
+__global__ void __launch_bounds__(512) gn_scale_shift_kernel(GnPlan g, float2* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float chan[1024 * 2];
+  __shared__ unsigned long long isum[1024 * 2];
   __shared__ float gstat[64 * 2];
   const int C = g.C0 + g.C1;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
-  for (int c = tid; c < C; c += 256) {
-    const long long* sp;
-    int ns, cs;
-    if (c < g.C0) { sp = g.stats0 + ((size_t)b * g.slots0 * g.C0 + c) * 2; ns = g.slots0; cs = g.C0; }
-    else { sp = g.stats1 + ((size_t)b * g.slots1 * g.C1 + (c - g.C0)) * 2; ns = g.slots1; cs = g.C1; }
-    long long a = 0, d = 0;
-    for (int k = 0; k < ns; ++k) {
-      const longlong2 v = *reinterpret_cast<const longlong2*>(sp + (size_t)k * cs * 2);
-      a += v.x;
-      d += v.y;
+  for (int i = tid; i < 2 * C; i += 512) isum[i] = 0ull;
+  __syncthreads();
+  {
+    const int n0 = g.slots0 * g.C0, n1 = g.slots1 * g.C1;
+    const long long* s0 = g.stats0 + (size_t)b * n0 * 2;
+    const long long* s1 = g.C1 ? g.stats1 + (size_t)b * n1 * 2 : nullptr;
+    for (int i = tid; i < n0 + n1; i += 512) {
+      const bool second = i >= n0;
+      const int k = second ? i - n0 : i;
+      const int c = second ? g.C0 + k % g.C1 : k % g.C0;
+      const longlong2 v = *reinterpret_cast<const longlong2*>((second ? s1 : s0) + (size_t)k * 2);
+      atomicAdd(&isum[2 * c], (unsigned long long)v.x);
+      atomicAdd(&isum[2 * c + 1], (unsigned long long)v.y);
     }
-    chan[2 * c] = (float)((double)a * STAT_FIXED_INV);
-    chan[2 * c + 1] = (float)((double)d * STAT_FIXED_INV);
   }
   __syncthreads();
   const int cg = C / g.groups;
   if (tid < g.groups) {
     float a = 0.f, d = 0.f;
-    for (int k = 0; k < cg; ++k) { a += chan[2 * (tid * cg + k)]; d += chan[2 * (tid * cg + k) + 1]; }
+    for (int k = 0; k < cg; ++k) {
+      a += (float)((double)(long long)isum[2 * (tid * cg + k)] * STAT_FIXED_INV);
+      d += (float)((double)(long long)isum[2 * (tid * cg + k) + 1] * STAT_FIXED_INV);
+    }
     const float inv_n = 1.0f / ((float)g.HW * (float)cg);
     const float mean = a * inv_n;
     const float var = fmaxf(d * inv_n - mean * mean, 0.f);
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(256) gn_scale_shift_kernel(GnPlan g, float2* _
     gstat[2 * tid + 1] = rsqrtf(var + 1e-5f);
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += 512) {
     const int grp = c / cg;
     const float sc = gstat[2 * grp + 1] * __ldg(g.gamma + c);
     out[(size_t)b * C + c] = make_float2(sc, __ldg(g.beta + c) - gstat[2 * grp] * sc);
@@ -223,7 +230,7 @@ void launch_gn_scale_shift(const GnPlan& g, float2* out, cudaStream_t s) {
   const int C = g.C0 + g.C1;
   REQUIRE(C <= 1024 && C % g.groups == 0 && g.groups <= 64, "GroupNorm: unsupported channel count");
   REQUIRE(g.stats0 && (g.C1 == 0 || g.stats1), "GroupNorm: missing channel statistics");
-  launch_pdl(gn_scale_shift_kernel, dim3(g.B), dim3(256), 0, s, g, out);
+  launch_pdl(gn_scale_shift_kernel, dim3(g.B), dim3(512), 0, s, g, out);
   CUDA_CHECK(cudaGetLastError());
 }
 
