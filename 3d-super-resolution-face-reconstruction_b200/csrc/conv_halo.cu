@@ -13,10 +13,10 @@ CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, v
 
 static int g_halo_sms = 148;
 
-template <int BN, int MT, bool GN, int GEO = 0>
+template <int BN, int MT, bool GN, int GEO = 0, int CG = 1>
 static void set_attr() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, GN, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  HaloSmem<BN, MT, GEO>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, GN, GEO, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<BN, MT, GEO, CG>::TOTAL));
 }
 
 void conv_halo_init_device() {
@@ -28,6 +28,9 @@ void conv_halo_init_device() {
   set_attr<16, 2, false>();  set_attr<16, 2, true>();
   set_attr<64, 1, false, 1>();  set_attr<64, 1, true, 1>();
   set_attr<128, 1, false, 1>(); set_attr<128, 1, true, 1>();
+  set_attr<64, 1, false, 0, 2>();  set_attr<64, 1, true, 0, 2>();
+  set_attr<128, 1, false, 0, 2>(); set_attr<128, 1, true, 0, 2>();
+  set_attr<256, 1, false, 0, 2>(); set_attr<256, 1, true, 0, 2>();
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -37,6 +40,24 @@ template <int BN, int MT, int GEO = 0>
 static void launch_halo(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
   if (gn) launch_pdl(conv_halo_kernel<BN, MT, true, GEO>, dim3(grid), dim3(halo_threads(BN)), HaloSmem<BN, MT, GEO>::TOTAL, s, p);
   else launch_pdl(conv_halo_kernel<BN, MT, false, GEO>, dim3(grid), dim3(halo_threads(BN)), HaloSmem<BN, MT, GEO>::TOTAL, s, p);
+}
+// CTA pairs (cta_group::2): a cluster of two CTAs per tile pair
+template <int BN>
+static void launch_halo_pair(const ConvHaloParams& p, bool gn, int grid, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(halo_threads(BN));
+  cfg.dynamicSmemBytes = HaloSmem<BN, 1, 0, 2>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (gn) CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, 1, true, 0, 2>, p));
+  else CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, 1, false, 0, 2>, p));
 }
 
 static bool geo1(int H, int W) { return H == 8 && W == 8; }   // two whole 8x8 images per tile
@@ -69,6 +90,8 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
     for (int tn = 1; tn <= 16; tn *= 2) {
       const long long total = seg_len / mt * units * tn;
       need = std::max(need, slots_needed(seg_len / mt, total, std::min<long long>(total, g_halo_sms)));
+      // CTA pairs: super tile = the pair's two tiles, one run per cluster, two slots per cluster
+      if (mt == 2) need = std::max(need, 2 * slots_needed(seg_len / 2, total, std::min<long long>(total, g_halo_sms / 2)));
     }
   }
   return need;
@@ -184,50 +207,66 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   // max(MMA cycles, L2->SM bytes / rate); a CTA runs ceil(super tiles / SMs) of them.
   const long long tiles_img = (long long)p.tiles_w * p.tiles_h;
   const long long m_tiles = tiles_img * p.num_par * p.units;
-  int bn = 0, mt = 0;
+  int bn = 0, mt = 0, cg = 1;
   {
     int fbn = 0, fmt = 0;
     if (const char* e = getenv("B200SR3_HALO_BN")) fbn = atoi(e);
     if (const char* e = getenv("B200SR3_HALO_MT")) fmt = atoi(e);
     double best = 1e30;
-    const int cand[6][2] = {{256, 1}, {128, 1}, {64, 2}, {64, 1}, {16, 2}, {16, 1}};
+    int fcg = 0;
+    if (const char* e = getenv("B200SR3_HALO_CG")) fcg = atoi(e);
+    int cg_min_bn = 64;
+    if (const char* e = getenv("B200SR3_HALO_CG_MIN_BN")) cg_min_bn = atoi(e);
+    const int cand[9][3] = {{256, 1, 2}, {128, 1, 2}, {64, 1, 2}, {256, 1, 1}, {128, 1, 1}, {64, 2, 1}, {64, 1, 1}, {16, 2, 1}, {16, 1, 1}};
+    // CTA pairs are opt-in (B200SR3_HALO_CG=2, optionally only for BLOCK_N >= B200SR3_HALO_CG_MIN_BN): in burst timing
+    // they are 0-60 % SLOWER than the one-CTA shapes on every layer of the R=128 UNet
+    // (profiles/r01e_cta_pair_halo_bench.txt) - the pair runs in lock step through cross-CTA barriers and gives up the
+    // MT=2 weight reuse that the Cout=64 layers rely on. Pass 0 looks for a pair shape, pass 1 for a one-CTA shape.
+    const bool pair_ok = fcg == 2 && !(g1 || tail || tiles_img % 2 != 0);
+    for (int pass = pair_ok ? 0 : 1; pass < 2 && bn == 0; ++pass)
     for (auto& c : cand) {
+      if ((c[2] == 2) != (pass == 0)) continue;
+      if (c[2] == 2 && c[0] < cg_min_bn) continue;
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
+      const int tiles_per_super = c[1] * c[2];
       if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
-      const double mma_cyc = c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : (c[0] == 64 ? 48.0 : 36.0));   // per MMA, measured
+      // cycles per (M=128 per CTA) MMA, measured; a CTA pair feeds (4 + N/64) KB per MMA instead of (4 + N/32) KB
+      const double mma_cyc = c[2] == 2 ? (c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : 40.0))
+                                       : (c[0] == 256 ? 128.0 : (c[0] == 128 ? 64.0 : (c[0] == 64 ? 48.0 : 36.0)));
       double per_super = 0.0;
       for (int i = 0; i < p.num_segs; ++i) {
         const double mma = p.seg[i].ntaps * c[1] * 4 * mma_cyc;
-        const double bytes = c[1] * (double)(g1 ? 25600 : HALO_BYTES) + p.seg[i].ntaps * c[0] * 128.0;
+        const double bytes = c[1] * (double)(g1 ? 25600 : HALO_BYTES) + p.seg[i].ntaps * c[0] * 128.0 / c[2];
         per_super += p.seg[i].cblocks * std::max(mma, bytes / 56.0);
       }
       per_super += 300.0 + c[1] * c[0] * 5.0;                                      // epilogue drain, not overlapped at the end
-      const long long supers = m_tiles / c[1] * (out.C / c[0]);
-      const double rounds = (double)((supers + g_halo_sms - 1) / g_halo_sms);
+      const long long supers = m_tiles / tiles_per_super * (out.C / c[0]);
+      const long long units_avail = g_halo_sms / c[2];
+      const double rounds = (double)((supers + units_avail - 1) / units_avail);
       const double cost = rounds * per_super;
-      if (cost < best) { best = cost; bn = c[0]; mt = c[1]; }
+      if (cost < best) { best = cost; bn = c[0]; mt = c[1]; cg = c[2]; }
     }
     REQUIRE(bn != 0, "halo conv: no tile shape fits (check B200SR3_HALO_BN / B200SR3_HALO_MT)");
   }
   p.tiles_n = out.C / bn;
-  p.total_super = (int)(m_tiles / mt * p.tiles_n);
-  p.seg_len_super = (int)(tiles_img * p.num_par / mt);
+  p.total_super = (int)(m_tiles / (mt * cg) * p.tiles_n);
+  p.seg_len_super = (int)(tiles_img * p.num_par / (mt * cg));
   {
     cuuint64_t dims[2] = {(cuuint64_t)w.k_total, (cuuint64_t)w.cout * p.num_par};
     cuuint64_t strides[1] = {(cuuint64_t)w.k_total * 2};
-    cuuint32_t box[2] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)(bn / cg)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_tiled(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, estr,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
   }
-  const int grid = std::min(p.total_super, g_halo_sms);
+  const int grid = cg * std::min(p.total_super, g_halo_sms / cg);
   if (const char* ab = getenv("B200SR3_CONV_ABLATE")) p.ablate = atoi(ab);
   if (stats) p.dbg = stats->dbg;
   if (stats && stats->partial) {
-    REQUIRE(slots_needed(p.seg_len_super, p.total_super, grid) <= stats->slots,
+    REQUIRE(cg * slots_needed(p.seg_len_super, p.total_super, grid / cg) <= stats->slots,
             "halo conv: statistics scratch has too few slots");
     p.stat_partial = stats->partial;
     p.stat_slots = stats->slots;
@@ -242,8 +281,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
   }
-  op.run = [pp, grid, bn, mt, any_gn, g1](cudaStream_t s) {
-    if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
+  op.run = [pp, grid, bn, mt, cg, any_gn, g1](cudaStream_t s) {
+    if (cg == 2) {
+      if (bn == 256) launch_halo_pair<256>(*pp, any_gn, grid, s);
+      else if (bn == 128) launch_halo_pair<128>(*pp, any_gn, grid, s);
+      else launch_halo_pair<64>(*pp, any_gn, grid, s);
+    } else if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
     else if (g1) launch_halo<64, 1, 1>(*pp, any_gn, grid, s);
     else if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);

@@ -113,12 +113,12 @@ struct alignas(64) ConvHaloParams {
 };
 
 #ifdef __CUDACC__
-template <int BLOCK_N, int MT, int GEO = 0>
+template <int BLOCK_N, int MT, int GEO = 0, int CG = 1>
 struct HaloSmem {
   static constexpr int A_STAGE = MT * HaloGeo<GEO>::STRIDE;
   static constexpr int AST = halo_a_stages(BLOCK_N, MT, GEO);
   static constexpr int A_BYTES = AST * A_STAGE;
-  static constexpr int W_STAGE = BLOCK_N * 128;
+  static constexpr int W_STAGE = (BLOCK_N / CG) * 128;           // a CTA of a cta_group::2 pair holds half the weight tile
   static constexpr int NSTG = (BLOCK_N == 256 || MT == 2) ? 1 : 2;   // staging slabs per epilogue warp
   static constexpr int ESETS = halo_esets(BLOCK_N);
   static constexpr int STG_BYTES = 4 * ESETS * NSTG * 4096;
@@ -150,6 +150,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// ---- cta_group::2 (CTA pair) helpers; semantics verified in tools/micro/umma_2cta.cu
+constexpr uint32_t HALO_PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {      // bar: shared::cluster address (any CTA of the cluster)
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {        // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -183,10 +224,18 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
 #define HDBG_ACC(i) do { if (p.dbg) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
 #define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
-template <int BLOCK_N, int MT, bool FUSE_GN, int GEO>
+// CG = 2: two CTAs of a cluster (one TPC) run ONE M = 256 tile pair with tcgen05 cta_group::2. Each CTA loads its own
+// halo, transforms it, and drains its own 128 accumulator rows, but only HALF of every weight tile: the pair shares the
+// B operand, which halves the weight bytes through each CTA's shared-memory port and cuts the operand bytes a CTA feeds
+// per MMA from (4 + N/32) KB to (4 + N/64) KB. The leader (rank 0) issues the MMAs; its barriers collect both CTAs'
+// weight loads (TMA in cta_group::2 form signals the leader's barrier), transform arrivals and epilogue releases;
+// tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
+template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1>
 __global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
-  using S = HaloSmem<BLOCK_N, MT, GEO>;
+  using S = HaloSmem<BLOCK_N, MT, GEO, CG>;
+  static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
+  constexpr bool XF = FUSE_GN || CG == 2;      // transform warps active (in a pair they also forward "halo landed" to the leader)
   using G = HaloGeo<GEO>;
   static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the two-image geometry runs plain convs, one tile at a time");
   constexpr int ESETS = S::ESETS;
@@ -222,7 +271,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   if (warp == LW + 1 && lane == 0) {
     for (int s = 0; s < AST; ++s) {
       ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_ready(s), 256);
+      ptx::mbar_init(a_ready(s), CG == 2 ? 16 : 256);      // pair: one arrival per transform warp of both CTAs
       ptx::mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < WST; ++s) {
@@ -231,24 +280,30 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     for (int b = 0; b < NBUF; ++b) {
       ptx::mbar_init(tmem_full(b), 1);
-      ptx::mbar_init(tmem_empty(b), 128 * ESETS);
+      ptx::mbar_init(tmem_empty(b), CG == 2 ? 8 : 128 * ESETS);   // pair: one arrival per epilogue warp of both CTAs
     }
     ptx::fence_barrier_init();
   }
-  if (warp == LW + 2) ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  if (warp == LW + 2) {
+    if (CG == 2) tmem_alloc_pair(tmem_slot, NBUF * MT * BLOCK_N);
+    else ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them
   ptx::tc_fence_after();
   pdl_wait();            // everything above overlapped the previous kernel's tail; its results are needed from here
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // contiguous run of super tiles; order: x tile fastest, y tile, parity, image, n tile
-  const int sup_begin = (int)(((long long)blockIdx.x * p.total_super) / gridDim.x);
-  const int sup_end = (int)(((long long)(blockIdx.x + 1) * p.total_super) / gridDim.x);
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;      // rank in the CTA pair; tile = 2 * super + rank
+  const int unit_id = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
+  const int sup_begin = (int)(((long long)unit_id * p.total_super) / num_units);
+  const int sup_end = (int)(((long long)(unit_id + 1) * p.total_super) / num_units);
   struct Tile { int n_tile, x0, y0, b, par; };
   auto decode = [&](int sup, int mt) {
-    int tile = sup * MT + mt;
+    int tile = (sup * MT + mt) * CG + (int)crank;
     Tile t;
     t.x0 = (tile % p.tiles_w) * HALO_TW; tile /= p.tiles_w;
     t.y0 = (tile % p.tiles_h) * HALO_TH; tile /= p.tiles_h;
@@ -298,16 +353,23 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int ws = 0; uint32_t wphase = 0;
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         const Tile t = decode(sup, 0);
-        const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N;
+        const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N + (int)crank * (BLOCK_N / CG);
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const HaloSeg seg = p.seg[sg];
           for (int cb = 0; cb < seg.cblocks; ++cb) {
             for (int tap = 0; tap < seg.ntaps; ++tap) {
               ptx::mbar_wait(w_empty(ws), wphase ^ 1u);
-              ptx::mbar_expect_tx(w_full(ws), (p.ablate & 4) ? 0 : S::W_STAGE);
-              if (!(p.ablate & 4))
-              ptx::tma_load_2d(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws),
-                               seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
+              if (CG == 2) {
+                // both halves of the tile complete on the LEADER's barrier, which the leader arms for both
+                if (crank == 0) ptx::mbar_expect_tx(w_full(ws), CG * S::W_STAGE);
+                tma_load_2d_pair(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws) & HALO_PEER_MASK,
+                                 seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
+              } else {
+                ptx::mbar_expect_tx(w_full(ws), (p.ablate & 4) ? 0 : S::W_STAGE);
+                if (!(p.ablate & 4))
+                  ptx::tma_load_2d(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws),
+                                   seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
+              }
               if (++ws == WST) { ws = 0; wphase ^= 1u; }
             }
           }
@@ -321,10 +383,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     // minimal: descriptors are (constant high word, low word advanced by adds), the tap window walks
     // the halo tile incrementally, and the NEXT weight stage's barrier is probed before this tap's
     // MMAs are issued so that its latency overlaps them.
-    if (ptx::elect_one()) {
+    if (crank == 0 && ptx::elect_one()) {
       constexpr uint32_t A_HI = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M, BLOCK_N);
+      const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M * CG, BLOCK_N);
       const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | 0x10000u;
       const uint32_t w_lo0 = (((smem_base + S::W_OFFSET) & 0x3FFFFu) >> 4) | 0x10000u;
       auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
@@ -349,7 +411,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           const uint32_t pix0 = ntaps == 9 ? 0u : (ntaps == 4 ? (uint32_t)((par >> 1) * G::PITCH + (par & 1)) : (uint32_t)(G::PITCH + 1));
           for (int cb = 0; cb < cblocks; ++cb) {
             HDBG_T0();
-            ptx::mbar_wait(FUSE_GN ? a_ready(as) : a_full(as), aphase);
+            ptx::mbar_wait(XF ? a_ready(as) : a_full(as), aphase);
             HDBG_ACC(0);
             uint32_t a_lo = a_lo0 + (uint32_t)as * (uint32_t)(S::A_STAGE >> 4) + pix0 * 8u;
             int tx = 0;
@@ -367,20 +429,25 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (G::STRIDE >> 4) + 2 * k), A_HI),
-                                 desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
+                for (int k = 0; k < 4; ++k) {
+                  if (CG == 2)
+                    umma_bf16_pair(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (G::STRIDE >> 4) + 2 * k), A_HI),
+                                   desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
+                  else
+                    ptx::umma_bf16(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (G::STRIDE >> 4) + 2 * k), A_HI),
+                                   desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
+                }
               }
-              ptx::umma_commit(wcur);
+              if (CG == 2) umma_commit_pair(wcur); else ptx::umma_commit(wcur);
               accum = 1;
               a_lo += 8u;
               if (++tx == ntx) { tx = 0; a_lo += (uint32_t)(G::PITCH - ntx) * 8u; }
             }
-            ptx::umma_commit(a_empty(as));
+            if (CG == 2) umma_commit_pair(a_empty(as)); else ptx::umma_commit(a_empty(as));
             if (++as == AST) { as = 0; aphase ^= 1u; }
           }
         }
-        ptx::umma_commit(tmem_full(buf));
+        if (CG == 2) umma_commit_pair(tmem_full(buf)); else ptx::umma_commit(tmem_full(buf));
       }
       // all of this CTA's MMAs are issued: only the last epilogue remains, let the next kernel's CTAs
       // be scheduled (they run their prologue and block in pdl_wait until this grid has completed)
@@ -555,17 +622,23 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
       // all of this thread's TMEM reads have completed: hand the accumulator back to the MMA warp
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tmem_empty(buf));
+      if (CG == 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty(buf) & HALO_PEER_MASK);      // the leader's barrier
+      } else {
+        ptx::mbar_arrive(tmem_empty(buf));
+      }
 
       if (do_stats) {
         const int seg = sup / p.seg_len_super;
         if (sup + 1 == sup_end || (sup + 1) / p.seg_len_super != seg) {
           // the CTA's run over this (n tile, image) segment ends: publish its partial sums. The four
           // warps' sums meet in the (drained) staging slabs: [column][sum|sq] int64 per warp.
-          const long long G = gridDim.x, T = p.total_super;
-          const int first_cta = (int)((((long long)seg * p.seg_len_super + 1) * G - 1) / T);
-          const int last_cta = (int)((((long long)(seg + 1) * p.seg_len_super) * G - 1) / T);
-          const int slot = (int)blockIdx.x - first_cta;
+          const long long GU = num_units, T = p.total_super;
+          const int first_unit = (int)((((long long)seg * p.seg_len_super + 1) * GU - 1) / T);
+          const int last_unit = (int)((((long long)(seg + 1) * p.seg_len_super) * GU - 1) / T);
+          const int slot = (unit_id - first_unit) * CG + (int)crank;       // a pair publishes two slots
+          const bool is_last = unit_id == last_unit && (int)crank == CG - 1;
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
           long long* mine = reinterpret_cast<long long*>(slab_gen);
@@ -588,7 +661,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               a += reinterpret_cast<const long long*>(smem_gen + S::STG_OFFSET + ww * (NSTG * 4096))[item];
             long long* dst = p.stat_partial + (((size_t)(t0.b + im) * p.stat_slots + slot) * p.Cout + n0) * 2 + within;
             *dst = a;
-            if ((int)blockIdx.x == last_cta)
+            if (is_last)
               for (int sl2 = slot + 1; sl2 < p.stat_slots; ++sl2) dst[(size_t)(sl2 - slot) * p.Cout * 2] = 0;
           }
           HALO_EPI_SYNC();
@@ -598,7 +671,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
 #undef HALO_EPI_SYNC
-  } else if (FUSE_GN && (warp < 4 || (warp >= 8 && warp < 12))) {
+  } else if (XF && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
     // thread -> (16-byte channel chunk j, pixels p_first + 32 i): its 8 channels' (scale, shift) sit in
     // registers for the whole halo tile; a warp touches 4 full 128-byte pixel rows per access. The
@@ -698,7 +771,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             }
             fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async reads
           }
-          ptx::mbar_arrive(a_ready(as));
+          if (CG == 2) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a_ready(as) & HALO_PEER_MASK);      // the leader's barrier
+          } else {
+            ptx::mbar_arrive(a_ready(as));
+          }
           HDBG_ACC(1);
           if (++as == AST) { as = 0; aphase ^= 1u; }
         }
@@ -709,7 +787,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == LW + 2) ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
+  if (CG == 2) cluster_sync_all();          // no CTA of the pair exits while the other may still signal it
+  if (warp == LW + 2) {
+    if (CG == 2) tmem_dealloc_pair(tmem_base, NBUF * MT * BLOCK_N);
+    else ptx::tmem_dealloc(tmem_base, NBUF * MT * BLOCK_N);
+  }
 }
 #endif  // __CUDACC__
 
