@@ -317,6 +317,8 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
     if (Cr0) srcs.push_back(HaloSource{make_act(r0, Cr0, false), 1, -1});
     if (Cr1) srcs.push_back(HaloSource{make_act(r1, Cr1, false), 1, -1});
     float2* gn = nullptr;
+    GnPlan gplan;
+    bool gn_in_kernel = false;
     if (has_gn) {
       gn = (float2*)dalloc((size_t)B * (C0 + C1) * sizeof(float2));
       GnPlan g;
@@ -327,7 +329,10 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       CUDA_CHECK(cudaMemcpyAsync(dg, gamma, (size_t)(C0 + C1) * sizeof(float), cudaMemcpyDefault, s));
       CUDA_CHECK(cudaMemcpyAsync(db, beta, (size_t)(C0 + C1) * sizeof(float), cudaMemcpyDefault, s));
       g.gamma = dg; g.beta = db;
-      launch_gn_scale_shift(g, gn, s);
+      gplan = g;
+      const char* tk = getenv("B200SR3_GN_TABLE_KERNEL");
+      if (tk && tk[0] == '1') launch_gn_scale_shift(g, gn, s);      // the separate-launch table (A/B)
+      else gn_in_kernel = true;                                      // default: the conv builds the table itself
     }
     Act out;
     out.B = B; out.C = Cout; out.H = up ? 2 * H : H; out.W = up ? 2 * W : W;
@@ -358,7 +363,7 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 16 * sizeof(unsigned long long)));
     }
     Op op = make_conv_halo_op("conv_block", srcs, up, pc, bias, 0, nullptr, out, gn, cin, swish != 0,
-                              (stats_out || timing) ? &st : nullptr);
+                              (stats_out || timing) ? &st : nullptr, nullptr, nullptr, gn_in_kernel ? &gplan : nullptr);
     op.run(s);
     launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
     CUDA_CHECK(cudaStreamSynchronize(s));

@@ -100,7 +100,7 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
-                     std::shared_ptr<ConvHaloParams>* params_out) {
+                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats) {
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
   const int PH = a0.H, PW = a0.W;
@@ -165,7 +165,8 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     }
     kblocks += sg.ntaps * sg.cblocks;
     any_gn |= s.gn_off >= 0;
-    if (s.gn_off >= 0) REQUIRE(gn != nullptr && s.gn_off + a.C <= gn_C, "halo conv: GroupNorm table too small");
+    if (s.gn_off >= 0)
+      REQUIRE((gn != nullptr || gn_from_stats != nullptr) && s.gn_off + a.C <= gn_C, "halo conv: GroupNorm table too small");
   }
   p.num_segs = (int)srcs.size();
   REQUIRE(k_short == w.k_total, "halo conv: packed weight K does not match the segment list");
@@ -179,6 +180,15 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.out = out.ptr;
   REQUIRE(!any_gn || gn_C <= 1024, "halo conv: the fused GroupNorm handles at most 1024 channels");
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
+  if (any_gn && gn_from_stats) {
+    const GnPlan& g = *gn_from_stats;
+    REQUIRE(g.C0 + g.C1 == gn_C && g.HW == PH * PW && g.B == out.B, "halo conv: GroupNorm plan does not match the sources");
+    REQUIRE(g.groups >= 1 && g.groups <= 32 && gn_C % g.groups == 0, "halo conv: the in-kernel GroupNorm table handles <= 32 groups");
+    REQUIRE(g.stats0 && (g.C1 == 0 || g.stats1) && g.gamma && g.beta, "halo conv: GroupNorm plan is missing statistics or affine parameters");
+    p.gn = nullptr;
+    p.gn_stats0 = g.stats0; p.gn_stats1 = g.stats1; p.gn_slots0 = g.slots0; p.gn_slots1 = g.slots1;
+    p.gn_C0 = g.C0; p.gn_groups = g.groups; p.gn_gamma = g.gamma; p.gn_beta = g.beta;
+  }
   // output maps for the epilogue's tensor stores: box = one warp's slab (64 channels x 8 x 4 pixels);
   // a folded upsample writes output parity (py, px) through a view with doubled pixel strides
   if (tail) {

@@ -92,9 +92,17 @@ struct alignas(64) ConvHaloParams {
   int bias_t_stride;
   const StepCtl* ctl;
   bf16* out;                       // NHWC [B][out_H][out_W][Cout]
-  const float2* gn;                // [B][gn_C] (scale, shift) of the fused GroupNorm (null: none)
+  const float2* gn;                // [B][gn_C] (scale, shift) of the fused GroupNorm (null: none, or built in-kernel)
   int gn_C;
   int gn_swish;
+  // In-kernel (scale, shift) table: the transform warps turn the producers' per-channel partial sums
+  // ([B][slots][C][2] int64 fixed point, as written by a conv epilogue) into the table of the current image themselves,
+  // which removes the gn_scale_shift launch that otherwise sits between every two convs (same arithmetic, same bits).
+  const long long* gn_stats0;      // channels [0, gn_C0) of the normalised (concatenated) input; null: use `gn`
+  const long long* gn_stats1;      // channels [gn_C0, gn_C)
+  int gn_slots0, gn_slots1, gn_C0, gn_groups;
+  const float* gn_gamma;           // [gn_C]
+  const float* gn_beta;
   long long* stat_partial;         // as ConvParams::stat_partial
   int stat_slots;
   // BLOCK_N == 16 ("tail"): the conv is final_conv (unet.py:233, Cout = out_channel <= 4 padded to 16) and
@@ -124,7 +132,8 @@ struct HaloSmem {
   static constexpr int STG_BYTES = 4 * ESETS * NSTG * 4096;
   // (scale, shift) of the current image (pair), <= 1024 channels; every 8-channel group is followed by
   // 16 bytes of padding so that the eight groups a warp reads at once fall into different banks
-  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10;
+  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10 + 512;      // + (mean, rstd) of <= 2 x 32 groups
+  static constexpr int GSTAT_OFFSET_IN_GN = HaloGeo<GEO>::IMGS * 1024 * 10;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
   static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
@@ -292,7 +301,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   __syncthreads();
   if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them
   ptx::tc_fence_after();
-  pdl_wait();            // everything above overlapped the previous kernel's tail; its results are needed from here
+  // Everything above overlapped the previous kernel's tail (programmatic dependent launch); its results are needed from
+  // here on - except by the weight producer, which only reads constants and starts filling its ring at once.
+  if (warp != LW + 1) pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -691,14 +702,64 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       Tile t[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
-      if (p.gn && t[0].b != tab_b) {
+      if (FUSE_GN && t[0].b != tab_b) {
         asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous table
-        for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
-          const int im = idx >= p.gn_C ? 1 : 0;
-          const int c = idx - im * p.gn_C;
-          float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
-          if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
-          gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;       // 10 float2 slots per 8 channels
+        if (p.gn_stats0) {
+          // (1) per-channel (sum, sum of squares): exact int64 sum over the producer's slots, then to float
+          const int C = p.gn_C, C0 = p.gn_C0;
+          for (int idx = tt; idx < IMGS * C; idx += 256) {
+            const int im = idx >= C ? 1 : 0;
+            const int c = idx - im * C;
+            const int b = min(t[0].b + im, p.B - 1);
+            const bool second = c >= C0;
+            const int cs = second ? C - C0 : C0, cl = second ? c - C0 : c;
+            const int slots = second ? p.gn_slots1 : p.gn_slots0;
+            const long long* sp = (second ? p.gn_stats1 : p.gn_stats0) + ((size_t)b * slots * cs + cl) * 2;
+            long long a = 0, d = 0;
+            for (int k = 0; k < slots; ++k) {
+              const longlong2 v = *reinterpret_cast<const longlong2*>(sp + (size_t)k * cs * 2);
+              a += v.x; d += v.y;
+            }
+            gtab[im * gn_pitch + c + 2 * (c >> 3)] =
+                make_float2((float)((double)a * STAT_FIXED_INV), (float)((double)d * STAT_FIXED_INV));
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          // (2) per-group mean and 1/std (groups may straddle the seam of a concat, hence per-channel sums)
+          float2* gstat = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET + S::GSTAT_OFFSET_IN_GN);
+          const int cg = C / p.gn_groups;
+          if (tt < IMGS * p.gn_groups) {
+            const int im = tt / p.gn_groups, g = tt - im * p.gn_groups;
+            float a = 0.f, d = 0.f;
+            for (int k = 0; k < cg; ++k) {
+              const int c = g * cg + k;
+              const float2 v = gtab[im * gn_pitch + c + 2 * (c >> 3)];
+              a += v.x; d += v.y;
+            }
+            const float inv_n = 1.0f / ((float)(p.H * p.W) * (float)cg);
+            const float mean = a * inv_n;
+            const float var = fmaxf(d * inv_n - mean * mean, 0.f);
+            gstat[tt] = make_float2(mean, rsqrtf(var + 1e-5f));
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          // (3) (scale, shift) = (rstd * gamma, beta - mean * rstd * gamma), pre-halved for the tanh form of Swish
+          for (int idx = tt; idx < IMGS * C; idx += 256) {
+            const int im = idx >= C ? 1 : 0;
+            const int c = idx - im * C;
+            const float2 ms = gstat[im * p.gn_groups + c / cg];
+            float2 v;
+            v.x = ms.y * __ldg(p.gn_gamma + c);
+            v.y = __ldg(p.gn_beta + c) - ms.x * v.x;
+            if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
+            gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+          }
+        } else if (p.gn) {
+          for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
+            const int im = idx >= p.gn_C ? 1 : 0;
+            const int c = idx - im * p.gn_C;
+            float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
+            if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
+            gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;       // 10 float2 slots per 8 channels
+          }
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
         tab_b = t[0].b;

@@ -495,7 +495,11 @@ void Engine::build_workspace(Workspace& ws) {
     return y;
   };
 
-  // (scale, shift) table of a GroupNorm whose apply (+Swish) runs inside the consuming halo conv
+  // GroupNorm whose apply (+Swish) runs inside the consuming halo conv. By default the conv also builds the
+  // (scale, shift) table of its current image from the producers' partial sums (conv_halo.cuh); with
+  // B200SR3_GN_TABLE_KERNEL=1 the table is a separate one-CTA-per-image launch (the earlier design, kept for A/B).
+  struct GnRef { const float2* tab = nullptr; std::shared_ptr<GnPlan> plan; };
+  static const bool table_kernel = [] { const char* e = getenv("B200SR3_GN_TABLE_KERNEL"); return e && e[0] == '1'; }();
   auto gn_table = [&](const std::string& name, const Act& x0, const Act* x1, const std::string& gkey) {
     auto g = std::make_shared<GnPlan>();
     g->C0 = x0.C; g->stats0 = x0.stats; g->slots0 = x0.stat_slots;
@@ -505,14 +509,20 @@ void Engine::build_workspace(Workspace& ws) {
     REQUIRE(C % G == 0, "GroupNorm: channels not divisible by norm_groups");
     g->gamma = T_(gkey + ".weight");
     g->beta = T_(gkey + ".bias");
-    float2* tab = (float2*)dalloc((size_t)B * C * sizeof(float2));
-    ws.ops.push_back(Op{name + ".gn_scale", false, [g, tab](cudaStream_t s) { launch_gn_scale_shift(*g, tab, s); }, 0.0, 0.0});
-    return tab;
+    GnRef r;
+    if (table_kernel || G > 32) {
+      float2* tab = (float2*)dalloc((size_t)B * C * sizeof(float2));
+      ws.ops.push_back(Op{name + ".gn_scale", false, [g, tab](cudaStream_t s) { launch_gn_scale_shift(*g, tab, s); }, 0.0, 0.0});
+      r.tab = tab;
+    } else {
+      r.plan = g;
+    }
+    return r;
   };
   // halo-resident conv (conv_halo.cuh): 3x3 main source(s) with the GroupNorm+Swish applied in shared
   // memory, raw 1x1 shortcut sources, GroupNorm statistics of the output from the epilogue
   auto conv_halo = [&](const std::string& name, const std::vector<HaloSource>& srcs, bool up, const PackedConv& w,
-                       const float* bias, int bias_stride, const float2* gn, int gn_C, bool want_stats) {
+                       const float* bias, int bias_stride, const GnRef& gn, int gn_C, bool want_stats) {
     const Act& a0 = srcs[0].act;
     Act probe;
     probe.B = B; probe.H = up ? 2 * a0.H : a0.H; probe.W = up ? 2 * a0.W : a0.W; probe.C = w.cout;
@@ -520,11 +530,12 @@ void Engine::build_workspace(Workspace& ws) {
     ConvStats st;
     st.partial = y.stats;
     st.slots = y.stat_slots;
-    ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn, gn_C, true,
-                                       want_stats ? &st : nullptr));
+    ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, true,
+                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get()));
     ws.n_conv++;
     return y;
   };
+  const GnRef no_gn;
 
   std::vector<Act> feats;
   Act cur;
@@ -541,7 +552,7 @@ void Engine::build_workspace(Workspace& ws) {
           ws.ops.push_back(Op{l.name + ".pack", false, [=](cudaStream_t s) {
             launch_head_pack(cond, xw, cc, oc, B, R, hdst, s);
           }});
-          cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, nullptr, 0, true);
+          cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, no_gn, 0, true);
           ws.ops.back().flops = 2.0 * B * R * R * (double)l.cout * 9.0 * l.c_x;      // reference graph: K = 9 * in_channel
           feats.push_back(cur);
           break;
@@ -569,7 +580,7 @@ void Engine::build_workspace(Workspace& ws) {
       case LayerKind::Up: {
         const PackedConv& pc = convs_.at(l.name + ".conv");
         if (use_halo_ && conv_halo_eligible(cur.H, cur.W, cur.C % 64 == 0, pc.cout))
-          cur = conv_halo(l.name, {HaloSource{cur, 9, -1}}, true, pc, pc.bias, 0, nullptr, 0, true);
+          cur = conv_halo(l.name, {HaloSource{cur, 9, -1}}, true, pc, pc.bias, 0, no_gn, 0, true);
         else
           cur = conv(l.name, cur, 9, 1, true, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H * 2, cur.W * 2, true);
         break;
@@ -592,12 +603,12 @@ void Engine::build_workspace(Workspace& ws) {
           // Block = GN -> Swish -> Conv (unet.py:80-91) as ONE kernel each: the GroupNorm apply runs on the
           // halo tile in shared memory; only the tiny (scale, shift) table is a separate launch
           const int cin = l.c_x + l.c_skip;
-          const float2* g1 = gn_table(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0");
+          const GnRef g1 = gn_table(l.name + ".block1", xin, is_up ? &skip : nullptr, rb + ".block1.block.0");
           std::vector<HaloSource> s1{HaloSource{xin, 9, 0}};
           if (is_up) s1.push_back(HaloSource{skip, 9, l.c_x});
           Act h = conv_halo(l.name + ".conv1", s1, false, c1, table_ + noise_off_.at(l.name), noise_total_, g1, cin,
                             true);
-          const float2* g2 = gn_table(l.name + ".block2", h, nullptr, rb + ".block2.block.0");
+          const GnRef g2 = gn_table(l.name + ".block2", h, nullptr, rb + ".block2.block.0");
           // the shortcut (res_conv 1x1, or identity) is one or two extra raw 1x1 K segments of this GEMM
           std::vector<HaloSource> s2{HaloSource{h, 9, 0}, HaloSource{xin, 1, -1}};
           if (is_up) s2.push_back(HaloSource{skip, 1, -1});
@@ -630,14 +641,14 @@ void Engine::build_workspace(Workspace& ws) {
       case LayerKind::Final: {
         if (use_halo_ && tail_pc_.w && conv_halo_eligible(cur.H, cur.W, cur.C % 64 == 0, 64)) {
           // final_conv = Block(GN -> Swish -> Conv 64 -> 3) + the sampler update as ONE halo conv launch
-          const float2* g = gn_table(l.name, cur, nullptr, l.name + ".block.0");
+          const GnRef g = gn_table(l.name, cur, nullptr, l.name + ".block.0");
           Act o16;
           o16.B = B; o16.H = cur.H; o16.W = cur.W; o16.C = 16;
           HaloTail tl;
           tl.x = ws.x; tl.eps_out = nullptr; tl.coefs = coefs_; tl.oc = oc;
           ws.ops.push_back(make_conv_halo_op(l.name + ".tail", {HaloSource{cur, 9, 0}}, false, tail_pc_,
-                                             T_(l.name + ".block.3.bias"), 0, ctl_, o16, g, cur.C, true, nullptr, &tl,
-                                             &ws.tail_halo));
+                                             T_(l.name + ".block.3.bias"), 0, ctl_, o16, g.tab, cur.C, true, nullptr, &tl,
+                                             &ws.tail_halo, g.plan.get()));
           ws.n_conv++;
           break;
         }

@@ -183,7 +183,8 @@ struct HaloTail {      // final_conv fused with the sampler update (conv_halo.cu
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats,
-                     const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr);
+                     const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr,
+                     const GnPlan* gn_from_stats = nullptr);   // non-null: the kernel builds the table itself (gn ignored)
 void conv_halo_init_device();
 
 }  // namespace b200sr3
