@@ -4,5 +4,6 @@ from .networks import define_G                      # noqa: F401
 from .diffusion import GaussianDiffusion, make_beta_schedule   # noqa: F401
 from .unet import UNet                              # noqa: F401
 from . import configs                               # noqa: F401
+from . import mica_handoff                          # noqa: F401
 
-__all__ = ["define_G", "GaussianDiffusion", "UNet", "make_beta_schedule", "configs"]
+__all__ = ["define_G", "GaussianDiffusion", "UNet", "make_beta_schedule", "configs", "mica_handoff"]

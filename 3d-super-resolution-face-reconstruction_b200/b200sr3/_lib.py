@@ -48,6 +48,9 @@ _SIGNATURES = {
     "b200sr3_conv_block": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                      _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                      C.POINTER(C.c_float), _P]),
+    "b200sr3_tensor2img": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "b200sr3_mica_handoff": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "b200sr3_tensor_blob": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -272,6 +272,35 @@ class GaussianDiffusion(nn.Module):
         return self.sample_batched(x_in, noise=noise, seed=seed)
 
     @torch.no_grad()
+    def super_resolution_samples(self, x_in, n_samples, noise=None, seed=None, max_batch=None):
+        """`n_samples` independent chains per conditioning image in ONE batched call.
+
+        The reference's evaluation loop draws `cfg.sample` (the -s flag, 15 in the paper's runs) chains for the same
+        LR input one after the other at B=1 (lib/trainer_temp.py:441-444 calling model/sr3d/model.py:366 test_val,
+        each a full super_resolution call). Chains are independent, so they stack along the batch: image i, sample k
+        sits at row i*n_samples + k. x_in [B,3,R,R] -> [B, n_samples, 3, R, R]. `noise` (optional, parity runs):
+        [T, B*n_samples, 3, R, R] in that row order; otherwise Philox with `seed`. `max_batch` bounds the rows per
+        launch chain (the workspace is sized per batch); every row's result is independent of the chunking."""
+        n = int(n_samples)
+        if n < 1:
+            raise ValueError("b200sr3: n_samples must be >= 1")
+        dev = self._sampling_device()
+        cond = self._as_input(x_in, dev)
+        rows = cond.repeat_interleave(n, dim=0)
+        total = rows.shape[0]
+        step = total if not max_batch else max(1, int(max_batch))
+        if noise is not None and step < total:
+            noise = self._as_input(noise, dev)
+        outs = []
+        for i, lo in enumerate(range(0, total, step)):
+            hi = min(total, lo + step)
+            nz = None if noise is None else noise[:, lo:hi].contiguous()
+            sd = None if seed is None else int(seed) + i
+            outs.append(self.sample_batched(rows[lo:hi].contiguous(), noise=nz, seed=sd))
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        return out.reshape((cond.shape[0], n) + tuple(out.shape[1:]))
+
+    @torch.no_grad()
     def sample_host(self, cond_host, out_host=None, seed=0):
         """End-to-end call on HOST tensors (pinned for full PCIe speed): cond is copied to the
         device, the full chain runs with Philox noise, the result is copied back; returns when

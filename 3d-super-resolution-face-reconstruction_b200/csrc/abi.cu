@@ -416,4 +416,18 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
   });
 }
 
+int b200sr3_tensor2img(const float* x, int B, int C, int H, int W, uint8_t* img, void* stream) {
+  return guarded([&] { launch_tensor2img(x, B, C, H, W, img, (cudaStream_t)stream); });
+}
+
+int b200sr3_mica_handoff(const uint8_t* img, int B, int R, uint8_t* up224, float* image224, float* arcface_blob,
+                         void* stream) {
+  return guarded([&] { launch_mica_handoff(img, B, R, up224, image224, arcface_blob, (cudaStream_t)stream); });
+}
+
+int b200sr3_tensor_blob(const float* x, int B, int R, float* arcface_blob, void* stream) {
+  return guarded([&] { launch_tensor_blob(x, B, R, arcface_blob, (cudaStream_t)stream); });
+}
+
+
 }  // extern "C"

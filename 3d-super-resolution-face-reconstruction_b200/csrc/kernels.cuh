@@ -105,4 +105,10 @@ void launch_nchw_to_nhwc(const float* src, bf16* dst, int B, int C, int H, int W
 void launch_nhwc_to_nchw(const bf16* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
 void launch_fill_f32(float* p, float v, long long n, cudaStream_t s);
 
+// ---- SR -> MICA hand-off (handoff.cu): core/metrics.py:16-42 tensor2img, model/sr3d/model.py:374 cv2.resize(224),
+// :127-131 cv2.dnn.blobFromImages(112, swapRB), :105-124 create_tensor_blob - bit-exact byte/integer kernels
+void launch_tensor2img(const float* x, int B, int C, int H, int W, uint8_t* img, cudaStream_t s);
+void launch_mica_handoff(const uint8_t* img, int B, int R, uint8_t* up, float* image, float* blob, cudaStream_t s);
+void launch_tensor_blob(const float* x, int B, int R, float* blob, cudaStream_t s);
+
 }  // namespace b200sr3

@@ -159,6 +159,31 @@ B200SR3_API int b200sr3_conv_block(int device, const float* x0, int C0, const fl
                    const float* wres, int B, int H, int W, int Cout, int upsample2x, float* y,
                    float* stats_out, int iters, float* avg_ms, void* stream);
 
+/* ---- SR -> MICA hand-off on the device. Stand-alone entry points (no handle): all pointers are
+ * device pointers, caller-owned; results are bit-identical to the reference's host round trip.
+ *
+ * b200sr3_tensor2img replaces core/metrics.py:16-42 (tensor2img): x fp32 NCHW [B,C,H,W] (C = 1 or 3, any range) ->
+ * img uint8 NHWC [B,H,W,C] = round_half_even(((clamp(x,-1,1)+1)/2)*255), image by image (the reference's 4-D branch
+ * builds a make_grid mosaic instead; callers on this path pass single images). */
+B200SR3_API int b200sr3_tensor2img(const float* x, int B, int C, int H, int W, uint8_t* img, void* stream);
+
+/* b200sr3_mica_handoff replaces model/sr3d/model.py:372-382 (and :484-485): for each uint8 RGB image [R,R,3]
+ *   up224        = cv2.resize(img, (224,224))                          uint8 NHWC [B,224,224,3]   (optional, may be NULL)
+ *   image224     = up224 / 255. as CHW                                 fp32 NCHW [B,3,224,224]    (optional; the reference
+ *                  holds this in float64, the consumer casts to fp32)
+ *   arcface_blob = cv2.dnn.blobFromImages([up224], 1/127.5, (112,112), (127.5,)*3, swapRB=True)[0] (:127-131)
+ *                                                                      fp32 NCHW [B,3,112,112]    (optional)
+ * OpenCV semantics (INTER_LINEAR fixed point; the 2x down-scale inside blobFromImages is a 2x2 box mean) are
+ * reproduced bit for bit. R = 448 (OpenCV's INTER_AREA shortcut on the first resize) is rejected. */
+B200SR3_API int b200sr3_mica_handoff(const uint8_t* img, int B, int R, uint8_t* up224, float* image224,
+                   float* arcface_blob, void* stream);
+
+/* b200sr3_tensor_blob replaces the model3 variant, model/sr3d/model.py:477-481: create_tensor_blob
+ * (:105-124) applied to core/metrics.py:44-50 tensor2tensor_img(x) * 255, i.e. float bilinear
+ * (align_corners=False) resize of (clamp(x)-derived pixel - 127.5)/127.5 to 112x112 with R and B swapped.
+ * x fp32 NCHW [B,3,R,R] -> arcface_blob fp32 NCHW [B,3,112,112]; float path, parity within 1e-5. */
+B200SR3_API int b200sr3_tensor_blob(const float* x, int B, int R, float* arcface_blob, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
