@@ -28,6 +28,7 @@ void conv_halo_init_device() {
   set_attr<16, 2, false>();  set_attr<16, 2, true>();
   set_attr<64, 1, false, 1>();  set_attr<64, 1, true, 1>();
   set_attr<128, 1, false, 1>(); set_attr<128, 1, true, 1>();
+  set_attr<64, 1, false, 2>();  set_attr<64, 1, true, 2>();
   set_attr<64, 1, false, 0, 2>();  set_attr<64, 1, true, 0, 2>();
   set_attr<128, 1, false, 0, 2>(); set_attr<128, 1, true, 0, 2>();
   set_attr<256, 1, false, 0, 2>(); set_attr<256, 1, true, 0, 2>();
@@ -61,10 +62,12 @@ static void launch_halo_pair(const ConvHaloParams& p, bool gn, int grid, cudaStr
 }
 
 static bool geo1(int H, int W) { return H == 8 && W == 8; }   // two whole 8x8 images per tile
+static bool geo2(int H, int W) { return H == 4 && W == 4; }   // five whole 4x4 images per tile
+static int geo_imgs(int H, int W) { return geo1(H, W) ? 2 : (geo2(H, W) ? 5 : 1); }
 
 bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout) {
   if (!c_multiple_of_64_all || cout % 64 != 0) return false;
-  return geo1(H, W) || ((H % HALO_TH == 0) && (W % HALO_TW == 0) && W >= 16 && H >= 16);
+  return geo1(H, W) || geo2(H, W) || ((H % HALO_TH == 0) && (W % HALO_TW == 0) && W >= 16 && H >= 16);
 }
 
 // CTAs a (n tile, image) segment of seg_len_super super tiles can be spread over when total_super
@@ -81,9 +84,10 @@ static int slots_needed(long long seg_len_super, long long total_super, long lon
 
 int conv_halo_stat_slots(const Act& out, bool upsample2x) {
   const int PH = upsample2x ? out.H / 2 : out.H, PW = upsample2x ? out.W / 2 : out.W;
-  const bool g1 = geo1(PH, PW);
+  const int gi = geo_imgs(PH, PW);
+  const bool g1 = gi > 1;
   const long long seg_len = (g1 ? 1 : (long long)(PH / HALO_TH) * (PW / HALO_TW)) * (upsample2x ? 4 : 1);
-  const long long units = g1 ? (out.B + 1) / 2 : out.B;
+  const long long units = (out.B + gi - 1) / gi;
   int need = 1;
   for (int mt = 1; mt <= 2; ++mt) {
     if (seg_len % mt) continue;
@@ -110,7 +114,9 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.num_par = upsample2x ? 4 : 1;
   REQUIRE(out.B == a0.B && out.H == (upsample2x ? 2 : 1) * PH && out.W == (upsample2x ? 2 : 1) * PW,
           "halo conv: output shape mismatch");
-  const bool g1 = geo1(PH, PW);
+  const bool g2 = geo2(PH, PW);
+  const bool g1 = geo1(PH, PW) || g2;      // a multi-image geometry (one tile per unit of 2 or 3 whole images)
+  const int gi = geo_imgs(PH, PW);
   REQUIRE(g1 || (PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16), "halo conv: unsupported spatial size");
   REQUIRE(!(g1 && tail), "halo conv: the tail runs on the one-image geometry");
   if (tail) {
@@ -137,7 +143,9 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
     cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
-    if (g1) {      // (C, W, B, H)-ordered view, box = 10 x 2 images x 10
+    if (g2) {             // natural order, box = the 5 x 5 grids (top zero row, left zero column) of five images
+      box[1] = 5; box[2] = 5; box[3] = 5;
+    } else if (g1) {      // (C, W, B, H)-ordered view, box = 10 x 2 images x 10
       std::swap(dims[2], dims[3]);
       std::swap(strides[1], strides[2]);
       box[2] = 2; box[3] = 10;
@@ -173,7 +181,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   REQUIRE(w.up_folded == upsample2x, "halo conv: weight packing / upsample mismatch");
   p.tiles_w = g1 ? 1 : PW / HALO_TW;
   p.tiles_h = g1 ? 1 : PH / HALO_TH;
-  p.units = g1 ? (out.B + 1) / 2 : out.B;
+  p.units = (out.B + gi - 1) / gi;
   p.B = out.B; p.H = PH; p.W = PW; p.Cout = out.C;
   p.out_H = out.H; p.out_W = out.W;
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
@@ -202,7 +210,9 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     cuuint64_t strides[3] = {(cuuint64_t)sc * out.C * 2, (cuuint64_t)sc * out.W * out.C * 2,
                              (cuuint64_t)out.H * out.W * out.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_TW, 4, 1};
-    if (g1) {      // (C, W, B, H)-ordered view; a warp's slab is 8 x 2 images x 2 rows
+    if (g2) {             // unused: the 4x4 geometry stores its interior rows from registers
+      box[1] = 4; box[2] = 4; box[3] = 1;
+    } else if (g1) {      // (C, W, B, H)-ordered view; a warp's slab is 8 x 2 images x 2 rows
       std::swap(dims[2], dims[3]);
       std::swap(strides[1], strides[2]);
       box[2] = 2; box[3] = 2;
@@ -239,6 +249,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       if (c[2] == 2 && c[0] < cg_min_bn) continue;
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
+      if (g2 && c[0] != 64) continue;
       if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
       const int tiles_per_super = c[1] * c[2];
       if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
@@ -248,7 +259,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       double per_super = 0.0;
       for (int i = 0; i < p.num_segs; ++i) {
         const double mma = p.seg[i].ntaps * c[1] * 4 * mma_cyc;
-        const double bytes = c[1] * (double)(g1 ? 25600 : HALO_BYTES) + p.seg[i].ntaps * c[0] * 128.0 / c[2];
+        const double bytes = c[1] * (double)(g2 ? 16000 : (g1 ? 25600 : HALO_BYTES)) + p.seg[i].ntaps * c[0] * 128.0 / c[2];
         per_super += p.seg[i].cblocks * std::max(mma, bytes / 56.0);
       }
       per_super += 300.0 + c[1] * c[0] * 5.0;                                      // epilogue drain, not overlapped at the end
@@ -291,12 +302,13 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
   }
-  op.run = [pp, grid, bn, mt, cg, any_gn, g1](cudaStream_t s) {
+  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2](cudaStream_t s) {
     if (cg == 2) {
       if (bn == 256) launch_halo_pair<256>(*pp, any_gn, grid, s);
       else if (bn == 128) launch_halo_pair<128>(*pp, any_gn, grid, s);
       else launch_halo_pair<64>(*pp, any_gn, grid, s);
-    } else if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
+    } else if (g2) launch_halo<64, 1, 2>(*pp, any_gn, grid, s);
+    else if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
     else if (g1) launch_halo<64, 1, 1>(*pp, any_gn, grid, s);
     else if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);

@@ -58,12 +58,26 @@ constexpr int HALO_MAX_SEGS = 4;
 // TWO whole images laid side by side in the halo tile - pixel (hy, image, hx) at hy*20 + image*10 + hx,
 // fetched by one TMA box over a (C, W, B, H)-ordered view - so that the 8-row groups (one image row of
 // one image each, ordered y-major, image-minor) are again exactly 10 pixels apart.
+// GEO 2 (4 x 4 images): a tile is FIVE whole images; accumulator row r is LINEAR pixel r of their 5x5 grids laid end to
+// end - pixel = image*25 + hy*5 + hx with hy = y+1, hx = x+1, i.e. each image carries its TOP zero row and LEFT zero
+// column only, exactly what one (C, W, H, B) box of 5 x 5 x 5 starting at (-1,-1) delivers. The right neighbour of x = 3
+// is then the next row's zero column and the row below y = 3 is the next image's zero row (for the last image: ten pixels
+// after the box that are zeroed once and never written), so every border read of an interior pixel lands on a zero. The
+// 8-row groups are dense (8 pixels apart) and tap (ky,kx) is the window shifted by (ky-1)*5 + (kx-1) pixels. 80 of the
+// 128 rows are outputs; zero-row / zero-column / tail rows compute garbage that is neither stored nor counted. A tile is
+// preceded by a 1 KB guard and its stage is long enough for the +6-pixel window of row 127.
 template <int GEO> struct HaloGeo;
 template <> struct HaloGeo<0> {
   static constexpr int PITCH = 10, ROWS = 18, NPIX = 180, BYTES = 180 * 128, STRIDE = 23552, IMGS = 1;
+  static constexpr int GROUP = 10, TMA_OFF = 0, MMA_OFF = 0;      // pixels between 8-row groups; byte offsets in a stage
 };
 template <> struct HaloGeo<1> {
   static constexpr int PITCH = 20, ROWS = 10, NPIX = 200, BYTES = 200 * 128, STRIDE = 26624, IMGS = 2;
+  static constexpr int GROUP = 10, TMA_OFF = 0, MMA_OFF = 0;
+};
+template <> struct HaloGeo<2> {
+  static constexpr int PITCH = 5, ROWS = 25, NPIX = 125, BYTES = 125 * 128, STRIDE = 18432, IMGS = 5;
+  static constexpr int GROUP = 8, TMA_OFF = 1024, MMA_OFF = 1024 - 6 * 128;      // tap (0,0) of row 0 is pixel -6
 };
 
 struct HaloSeg {
@@ -132,7 +146,7 @@ struct HaloSmem {
   static constexpr int STG_BYTES = 4 * ESETS * NSTG * 4096;
   // (scale, shift) of the current image (pair), <= 1024 channels; every 8-channel group is followed by
   // 16 bytes of padding so that the eight groups a warp reads at once fall into different banks
-  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10 + 512;      // + (mean, rstd) of <= 2 x 32 groups
+  static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10 + 2048;     // + (mean, rstd) of <= 5 x 32 groups
   static constexpr int GSTAT_OFFSET_IN_GN = HaloGeo<GEO>::IMGS * 1024 * 10;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
@@ -143,7 +157,7 @@ struct HaloSmem {
   static constexpr int BAR_OFFSET = GN_OFFSET + GN_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static_assert(W_STAGES >= 3, "weight ring too shallow");
-  static_assert(BLOCK_N * 16 * HaloGeo<GEO>::IMGS <= 4096, "statistics hand-over must fit one slab");
+  static_assert(BLOCK_N * 16 * HaloGeo<GEO>::IMGS <= NSTG * 4096, "statistics hand-over must fit a warp's slabs");
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -246,7 +260,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
   constexpr bool XF = FUSE_GN || CG == 2;      // transform warps active (in a pair they also forward "halo landed" to the leader)
   using G = HaloGeo<GEO>;
-  static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the two-image geometry runs plain convs, one tile at a time");
+  static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the multi-image geometries run plain convs, one tile at a time");
+  static_assert(GEO != 2 || BLOCK_N == 64, "the 4x4 geometry runs BLOCK_N = 64");
   constexpr int ESETS = S::ESETS;
   // warp groups: 0 = transform A, 1 = epilogue A, 2 = transform B, [3 = epilogue B], last = single-thread roles
   constexpr int LW = 4 * (2 + ESETS);        // first warp of the last group: LW+0 halo producer, +1 weight producer,
@@ -296,6 +311,15 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   if (warp == LW + 2) {
     if (CG == 2) tmem_alloc_pair(tmem_slot, NBUF * MT * BLOCK_N);
     else ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  }
+  if (GEO == 2) {
+    // pixels 125 .. 134 of every stage: the zero row below the last image (TMA never writes them, nobody else does)
+    for (int idx = (int)threadIdx.x; idx < AST * 10 * 8; idx += (int)blockDim.x) {
+      const int st = idx / 80, rem = idx - st * 80;
+      *reinterpret_cast<uint4*>(smem_gen + st * S::A_STAGE + G::TMA_OFF + (G::NPIX + rem / 8) * 128 + (rem % 8) * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -347,6 +371,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               if (GEO == 0)
                 ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
                                  cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
+              else if (GEO == 2)      // natural (C, W, H, B) order: the 5 x 5 grids of five images, end to end
+                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE + G::TMA_OFF, &p.a_map[seg.map], a_full(as),
+                                 cb * CONV_BLOCK_K, -1, -1, t[m].b);
               else      // view ordered (C, W, B, H): both images of the pair in one box
                 ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
                                  cb * CONV_BLOCK_K, -1, t[m].b, -1);
@@ -395,10 +422,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     // the halo tile incrementally, and the NEXT weight stage's barrier is probed before this tap's
     // MMAs are issued so that its latency overlaps them.
     if (crank == 0 && ptx::elect_one()) {
-      constexpr uint32_t A_HI = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t A_HI = (uint32_t)((G::GROUP * 128) >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t idesc = ptx::make_idesc_bf16(CONV_BLOCK_M * CG, BLOCK_N);
-      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t a_lo0 = (((smem_base + G::MMA_OFF) & 0x3FFFFu) >> 4) | 0x10000u;
       const uint32_t w_lo0 = (((smem_base + S::W_OFFSET) & 0x3FFFFu) >> 4) | 0x10000u;
       auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
       int as = 0, ws = 0;
@@ -538,7 +565,6 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #define HALO_EPI_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(128 * ESETS) : "memory")
     const int eset = warp >= 12 ? 1 : 0;                   // which epilogue set this warp belongs to
     const int tid_e = (int)threadIdx.x - (eset ? 256 : 128);     // 0 .. 128*ESETS-1
-    const uint32_t slab_u32 = smem_base + S::STG_OFFSET + (eset * 4 + wq) * (NSTG * 4096);
     uint8_t* slab_gen = smem_gen + S::STG_OFFSET + (eset * 4 + wq) * (NSTG * 4096);
     int unit = 0;                                          // 64-channel units seen so far (same count in every set)
     const bool do_stats = p.stat_partial != nullptr;
@@ -546,13 +572,31 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
     constexpr int IMGS = G::IMGS;
     // this lane's columns (2l, 2l+1) of each 64-channel chunk, per image of the tile: sum0, sum1, sq0, sq1
-    long long acc[IMGS][NCH][4];
+    constexpr int NACC = GEO == 2 ? 2 : IMGS;      // GEO 2: a warp's rows touch at most two images
+    long long acc[NACC][NCH][4];
 #pragma unroll
-    for (int im = 0; im < IMGS; ++im)
+    for (int im = 0; im < NACC; ++im)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) acc[im][c][0] = acc[im][c][1] = acc[im][c][2] = acc[im][c][3] = 0;
     // where lane l finds columns (2l, 2l+1) of slab row r: chunk (l >> 2) ^ (r & 7), word l & 3
     const uint32_t col_chunk = (uint32_t)(lane >> 2), col_word = (uint32_t)(lane & 3) * 4u;
+
+    // GEO 2: this warp's 32 accumulator rows are linear pixels 32 wq .. 32 wq + 31 of the five 5x5 grids: they belong to
+    // image g2_first (rows < g2_rb) and image g2_first + 1, and only interior pixels (bit set in g2_valid) are outputs.
+    // acc[0] / acc[1] then hold the sums of the warp's first / second image. Interior rows are stored straight from
+    // registers (128 contiguous bytes per row and 64-channel chunk): a tensor store whose box starts at (-1,-1) to clip
+    // the ring faults on this part ("illegal instruction"), and the level is far too small for the store path to matter.
+    int g2_first = 0, g2_rb = 32;
+    uint32_t g2_valid = 0u;
+    if (GEO == 2) {
+      g2_first = (32 * wq) / 25;
+      g2_rb = 25 * (g2_first + 1) - 32 * wq;
+      for (int r = 0; r < 32; ++r) {
+        const int px = 32 * wq + r, q = px % 25;
+        if (px < G::NPIX && q >= 5 && q % 5 != 0) g2_valid |= 1u << r;
+      }
+    }
+    auto data_off = [&](int st) { return (eset * 4 + wq) * (NSTG * 4096) + st * 4096; };
 
     int it = 0, stg = 0;
     HDBG_DECL();
@@ -572,11 +616,21 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
           if (ESETS == 2 && ((unit++ & 1) != eset)) continue;      // the other set's unit
-          const uint32_t sl = slab_u32 + (uint32_t)stg * 4096u;
-          uint8_t* slg = slab_gen + stg * 4096;
+          const uint32_t sl = smem_base + S::STG_OFFSET + (uint32_t)data_off(stg);
+          uint8_t* slg = smem_gen + S::STG_OFFSET + data_off(stg);
           // the tensor store that last read this slab must have finished reading it
           if (lane == 0) bulk_wait_read<NSTG - 1>();
           __syncwarp();
+          bf16* g2_dst = nullptr;             // GEO 2: this thread's output row in global memory (null: not an output)
+          if (GEO == 2 && ((g2_valid >> lane) & 1u) && !(p.ablate & 1)) {
+            const int img = g2_first + (lane >= g2_rb ? 1 : 0);
+            const int q = (32 * wq + lane) % 25, y = q / 5 - 1, x = q % 5 - 1;
+            if (t.b + img < p.B) {
+              const int sc = p.num_par == 4 ? 2 : 1;
+              const int oy = sc * y + (t.par >> 1), ox = sc * x + (t.par & 1);
+              g2_dst = p.out + (((size_t)(t.b + img) * p.out_H + oy) * p.out_W + ox) * p.Cout + n0 + cc * 64;
+            }
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
@@ -598,17 +652,38 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(slg + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(f + 8 * j);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = pack8(f + 8 * j);
+              *reinterpret_cast<uint4*>(slg + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pk;
+              if (GEO == 2 && g2_dst) *reinterpret_cast<uint4*>(g2_dst + (half * 4 + j) * 8) = pk;
+            }
           }
           fence_proxy_async_smem();       // generic-proxy writes -> visible to the TMA store
-          __syncwarp();
-          if (lane == 0 && !(p.ablate & 1)) {
-            if (GEO == 0) tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
-            else tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, 0, t.b, 2 * wq);      // (C, W, B, H) view
-            bulk_commit();
+          if (GEO == 2) {
+            __syncwarp();                   // rows were stored from registers; the slab only feeds the statistics
+          } else {
+            __syncwarp();
+            if (lane == 0 && !(p.ablate & 1)) {
+              if (GEO == 0) tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
+              else tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, 0, t.b, 2 * wq);      // (C, W, B, H) view
+              bulk_commit();
+            }
           }
-          if (do_stats && !(p.ablate & 32)) {
+          if (GEO == 2 && do_stats && !(p.ablate & 32)) {
+            // every element goes to fixed point on its own: which rows of an image a warp sees depends on the image's
+            // place in the tile, and float partial sums would make a face's statistics depend on its batch position
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(slg + r * 128 + (((col_chunk ^ (uint32_t)(r & 7)) << 4) | col_word));
+              const bool valid = (g2_valid >> r) & 1u;           // select, never multiply: border rows may hold NaN
+              const float lo = valid ? __uint_as_float(w << 16) : 0.f, hi = valid ? __uint_as_float(w & 0xffff0000u) : 0.f;
+              const long long i0 = __float2ll_rn(lo * STAT_FIXED_SCALE), i1 = __float2ll_rn(hi * STAT_FIXED_SCALE);
+              const long long i2 = __float2ll_rn(lo * lo * STAT_FIXED_SCALE), i3 = __float2ll_rn(hi * hi * STAT_FIXED_SCALE);
+              if (r >= g2_rb) { acc[1][cc][0] += i0; acc[1][cc][1] += i1; acc[1][cc][2] += i2; acc[1][cc][3] += i3; }
+              else { acc[0][cc][0] += i0; acc[0][cc][1] += i1; acc[0][cc][2] += i2; acc[0][cc][3] += i3; }
+            }
+          }
+          if (GEO != 2 && do_stats && !(p.ablate & 32)) {
             float s0[IMGS], s1[IMGS], q0[IMGS], q1[IMGS];
 #pragma unroll
             for (int im = 0; im < IMGS; ++im) s0[im] = s1[im] = q0[im] = q1[im] = 0.f;
@@ -658,10 +733,19 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
             for (int cc = 0; cc < NCH; ++cc) {
               const int col = im * BLOCK_N + cc * 64 + 2 * lane;
-              *reinterpret_cast<longlong2*>(mine + col * 2) = make_longlong2(acc[im][cc][0], acc[im][cc][2]);
-              *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(acc[im][cc][1], acc[im][cc][3]);
-              acc[im][cc][0] = acc[im][cc][1] = acc[im][cc][2] = acc[im][cc][3] = 0;
+              long long v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (GEO == 2) v[k] = im == g2_first ? acc[0][cc][k] : (im == g2_first + 1 ? acc[1][cc][k] : 0ll);
+                else v[k] = acc[im < NACC ? im : 0][cc][k];
+              }
+              *reinterpret_cast<longlong2*>(mine + col * 2) = make_longlong2(v[0], v[2]);
+              *reinterpret_cast<longlong2*>(mine + col * 2 + 2) = make_longlong2(v[1], v[3]);
             }
+#pragma unroll
+          for (int im = 0; im < NACC; ++im)
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) acc[im][cc][0] = acc[im][cc][1] = acc[im][cc][2] = acc[im][cc][3] = 0;
           HALO_EPI_SYNC();
           for (int item = tid_e; item < IMGS * 2 * BLOCK_N; item += 128 * ESETS) {
             const int im = item / (2 * BLOCK_N), within = item - im * 2 * BLOCK_N;
@@ -708,7 +792,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           // (1) per-channel (sum, sum of squares): exact int64 sum over the producer's slots, then to float
           const int C = p.gn_C, C0 = p.gn_C0;
           for (int idx = tt; idx < IMGS * C; idx += 256) {
-            const int im = idx >= C ? 1 : 0;
+            const int im = idx / C;
             const int c = idx - im * C;
             const int b = min(t[0].b + im, p.B - 1);
             const bool second = c >= C0;
@@ -743,7 +827,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           asm volatile("bar.sync 2, 256;" ::: "memory");
           // (3) (scale, shift) = (rstd * gamma, beta - mean * rstd * gamma), pre-halved for the tanh form of Swish
           for (int idx = tt; idx < IMGS * C; idx += 256) {
-            const int im = idx >= C ? 1 : 0;
+            const int im = idx / C;
             const int c = idx - im * C;
             const float2 ms = gstat[im * p.gn_groups + c / cg];
             float2 v;
@@ -754,7 +838,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           }
         } else if (p.gn) {
           for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
-            const int im = idx >= p.gn_C ? 1 : 0;
+            const int im = idx / p.gn_C;
             const int c = idx - im * p.gn_C;
             float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
             if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
@@ -767,11 +851,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       for (int sg = 0; sg < p.num_segs; ++sg) {
         const HaloSeg seg = p.seg[sg];
         for (int cb = 0; cb < seg.cblocks; ++cb) {
-          float sc[IMGS][8], sh[IMGS][8];
+          constexpr int NTAB = GEO == 2 ? 1 : IMGS;      // GEO 2 fetches (scale, shift) per pixel item instead
+          float sc[NTAB][8], sh[NTAB][8];
           HDBG_T0();
-          if (seg.gn_off >= 0) {
+          if (seg.gn_off >= 0 && GEO != 2) {
 #pragma unroll
-            for (int im = 0; im < IMGS; ++im) {
+            for (int im = 0; im < NTAB; ++im) {
               const int c0 = seg.gn_off + cb * CONV_BLOCK_K + j * 8;
               const float4* g4 = reinterpret_cast<const float4*>(gtab + im * gn_pitch + c0 + 2 * (c0 >> 3));
 #pragma unroll
@@ -791,8 +876,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               // tiles or is zero padding). GEO 1: only the 2 x 64 image pixels are visited - the ring is
               // all padding. All loads are issued before any math: a warp must cover LDS + MUFU latency
               // with its own instruction-level parallelism.
-              constexpr int NCHK = GEO == 0 ? (G::NPIX + 31) / 32 : 4;
-              uint8_t* tile = smem_gen + as * S::A_STAGE + m * G::STRIDE;
+              constexpr int NCHK = GEO == 0 ? (G::NPIX + 31) / 32 : (GEO == 1 ? 4 : 3);
+              uint8_t* tile = smem_gen + as * S::A_STAGE + m * G::STRIDE + G::TMA_OFF;
               const int gx0 = t[m].x0 - 1, gy0 = t[m].y0 - 1;
               uint4 v[NCHK];
               uint4* ptr[NCHK];
@@ -806,11 +891,16 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                   const int hy = px / G::PITCH, hx = px - hy * G::PITCH;
                   img[i] = 0;
                   ok[i] = px < G::NPIX && (unsigned)(gy0 + hy) < (unsigned)p.H && (unsigned)(gx0 + hx) < (unsigned)p.W;
-                } else {
+                } else if (GEO == 1) {
                   const int q = p_first + 32 * i;                       // (y, image, x) = (q >> 4, (q >> 3) & 1, q & 7)
                   img[i] = (q >> 3) & 1;
                   px = ((q >> 4) + 1) * G::PITCH + img[i] * 10 + (q & 7) + 1;
                   ok[i] = t[m].b + img[i] < p.B;
+                } else {
+                  const int q = p_first + 32 * i;                       // (image, y, x) = (q >> 4, (q >> 2) & 3, q & 3), q < 80
+                  img[i] = min(q >> 4, IMGS - 1);
+                  px = img[i] * 25 + (((q >> 2) & 3) + 1) * G::PITCH + (q & 3) + 1;
+                  ok[i] = q < 80 && t[m].b + img[i] < p.B;
                 }
                 ptr[i] = reinterpret_cast<uint4*>(tile + px * 128 + ((j ^ (px & 7)) << 4));
                 v[i] = ok[i] ? *ptr[i] : make_uint4(0u, 0u, 0u, 0u);
@@ -819,10 +909,19 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               for (int i = 0; i < NCHK; ++i) {
                 float f[8];
                 unpack8(v[i], f);
+                if (GEO == 2) {      // this item's image: its 8 channels' (scale, shift) from the staged table
+                  const int c0 = seg.gn_off + cb * CONV_BLOCK_K + j * 8;
+                  const float4* g4 = reinterpret_cast<const float4*>(gtab + img[i] * gn_pitch + c0 + 2 * (c0 >> 3));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float4 tv = g4[k];
+                    sc[0][2 * k] = tv.x; sh[0][2 * k] = tv.y; sc[0][2 * k + 1] = tv.z; sh[0][2 * k + 1] = tv.w;
+                  }
+                }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const float scv = (IMGS == 2 && img[i]) ? sc[IMGS - 1][e] : sc[0][e];
-                  const float shv = (IMGS == 2 && img[i]) ? sh[IMGS - 1][e] : sh[0][e];
+                  float scv = sc[0][e], shv = sh[0][e];
+                  if (GEO == 1 && img[i] == 1) { scv = sc[NTAB - 1][e]; shv = sh[NTAB - 1][e]; }
                   const float h = fmaf(f[e], scv, shv);
                   // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
                   f[e] = do_swish ? fmaf(h, tanh_approx(h), h) : h;

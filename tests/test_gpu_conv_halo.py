@@ -31,6 +31,12 @@ CASES = [
     (3, 128, 64, 128, 64, 8, 8, 128, 1, 0),         # ... odd batch: the last pair is half empty
     (5, 64, 0, 0, 0, 8, 8, 64, 0, 0),
     (3, 128, 0, 0, 0, 8, 8, 128, 0, 1),             # folded upsample 8 -> 16
+    (6, 512, 0, 512, 0, 4, 4, 512, 1, 0),           # 4x4 images: five images per tile (linear 5x5-grid rows)
+    (7, 512, 512, 512, 512, 4, 4, 512, 1, 0),       # ... concat + shortcut, batch not a multiple of 5
+    (1, 64, 0, 0, 0, 4, 4, 64, 0, 0),
+    (5, 128, 64, 0, 0, 4, 4, 128, 1, 0),
+    (4, 128, 0, 0, 0, 4, 4, 128, 0, 1),             # folded upsample 4 -> 8
+    (11, 64, 0, 64, 0, 4, 4, 64, 1, 0),             # three tiles, the last one holds a single image
 ]
 SHAPES = [(0, 0), (64, 1), (64, 2), (128, 1), (256, 1)]
 
@@ -99,7 +105,9 @@ def test_block_matches_torch(case):
     # (a folded upsample pre-sums the 3x3 weights in fp32 and rounds once, the reference rounds each
     # weight: a per-channel systematic difference that grows with n, not sqrt(n))
     assert float(err[..., 0].max()) <= 4e-3 * rms * n ** 0.5 * 4 + 1e-2 + (3e-3 * rms * n if case[9] else 0)
-    assert float(err[..., 1].max()) <= 1e-2 * rms * rms * n
+    # sum of squares of the bf16-ROUNDED output: each y carries <= 2^-9 relative rounding error, i.e. 2^-8 on y^2 (this
+    # term does not average out over the 16 pixels of a 4x4 image), plus the accumulation noise bound used above
+    assert bool((err[..., 1] <= 2 ** -7 * s_ref[..., 1] + 1e-2 * rms * rms * n).all())
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "bn%d_mt%d" % s)
@@ -149,7 +157,7 @@ def test_block_properties_at_baseline_size():
 
 def test_block_rejects_bad_shapes():
     from b200sr3 import _lib
-    x = torch.zeros(1, 64, 4, 4, device="cuda")         # below every tile geometry
+    x = torch.zeros(1, 64, 2, 2, device="cuda")         # below every tile geometry
     w = torch.zeros(64, 64, 3, 3, device="cuda")
     b = torch.zeros(64, device="cuda")
     with pytest.raises(_lib.B200Error):
