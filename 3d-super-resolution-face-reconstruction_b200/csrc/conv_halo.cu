@@ -182,6 +182,8 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.tiles_w = g1 ? 1 : PW / HALO_TW;
   p.tiles_h = g1 ? 1 : PH / HALO_TH;
   p.units = (out.B + gi - 1) / gi;
+  p.inv_tiles_w = 1.0f / (float)p.tiles_w; p.inv_tiles_h = 1.0f / (float)p.tiles_h;
+  p.inv_num_par = 1.0f / (float)p.num_par; p.inv_units = 1.0f / (float)p.units;
   p.B = out.B; p.H = PH; p.W = PW; p.Cout = out.C;
   p.out_H = out.H; p.out_W = out.W;
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
@@ -284,7 +286,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
   }
   const int grid = cg * std::min(p.total_super, g_halo_sms / cg);
+  REQUIRE((long long)p.total_super * (grid / cg + 1) < (1ll << 31) && m_tiles * p.tiles_n < (1ll << 22),
+          "halo conv: too many tiles for the kernel's 32-bit / float-reciprocal tile arithmetic");
   if (const char* ab = getenv("B200SR3_CONV_ABLATE")) p.ablate = atoi(ab);
+  p.pdl = pdl_enabled() ? 1 : 0;
   if (stats) p.dbg = stats->dbg;
   if (stats && stats->partial) {
     REQUIRE(cg * slots_needed(p.seg_len_super, p.total_super, grid / cg) <= stats->slots,

@@ -99,6 +99,7 @@ struct alignas(64) ConvHaloParams {
   int tiles_w, tiles_h;            // 8x16 tiles per image over the pixel space the tiles walk
   int B, H, W, Cout;               // pixel space the tiles walk (the SOURCE grid when num_par == 4)
   int units;                       // images (GEO 0) or image pairs (GEO 1) the tile index walks
+  float inv_tiles_w, inv_tiles_h, inv_num_par, inv_units;      // 1 / x of the four divisors of the tile decode
   int out_H, out_W;
   int tiles_n, total_super;        // N tiles; super tiles (MT tiles each) in the launch
   int seg_len_super;               // super tiles per (n tile, image) = tiles_w*tiles_h*num_par/MT
@@ -129,6 +130,7 @@ struct alignas(64) ConvHaloParams {
   // measurement only (B200SR3_CONV_ABLATE bit mask; results are then wrong): 1 = no global stores,
   // 2 = transform arrives without touching the tile, 4 = no weight loads, 8 = no halo loads,
   // 16 = no TMEM loads, 32 = no statistics math
+  int pdl;                         // launched with the programmatic-dependent-launch attribute (B200SR3_PDL=1)
   int ablate;
   // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv_block): [grid][16] cycle counters
   unsigned long long* dbg;
@@ -247,6 +249,105 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
 #define HDBG_ACC(i) do { if (p.dbg) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
 #define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
+// (scale, shift) table of the fused GroupNorm for the IMGS images starting at image b0, built by the 256 transform threads
+// (tt = 0..255) into shared memory: gtab[im * gn_pitch + c + 2 * (c >> 3)] (10 float2 slots per 8 channels: the eight
+// 64-byte groups a warp reads at once fall into different banks).
+// From the producers' statistics it is ONE pass with no intermediate barrier: TPG adjacent lanes own a (image, group).
+// Lane s takes the group's channels s, s + TPG, ...: for each it adds up the producer's int64 partial sums (exact, any
+// number of slots), converts to float and accumulates the group sums; a butterfly over the TPG lanes gives every lane
+// the group's mean and 1/std; the lane then writes (scale, shift) = (rstd * gamma, beta - mean * rstd * gamma) of its
+// channels (pre-halved for the tanh form of Swish). gamma / beta are requested together with the statistics, so the
+// table costs one global round trip. The summation order is fixed by the lane mapping: a face's table does not depend
+// on its batch or tile. Statistics are read through L2 only (nothing stale in L1 under programmatic dependent launch).
+template <int IMGS>
+__device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, float2* gtab, int gn_pitch, int tt, int b0,
+                                                    bool do_swish) {
+  asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous table
+  if (p.gn_stats0) {
+    const int C = p.gn_C, C0 = p.gn_C0;
+    const int cg = C / p.gn_groups;
+    constexpr int TPG = IMGS == 1 ? 8 : (IMGS == 2 ? 4 : 1);
+    constexpr int KEEP = 4;                       // channels per lane whose gamma / beta stay in registers
+    const int gi = tt / TPG, sub = tt - gi * TPG;
+    const bool live = gi < IMGS * p.gn_groups;
+    int im = 0, g = live ? gi : 0;
+    while (g >= p.gn_groups) { g -= p.gn_groups; ++im; }
+    const int b = min(b0 + im, p.B - 1);
+    float a = 0.f, d = 0.f, gam[KEEP], bet[KEEP];
+#pragma unroll
+    for (int q = 0; q < KEEP; ++q) gam[q] = bet[q] = 0.f;
+    auto chan_sums = [&](int c, float& fa, float& fd) {
+      const bool second = c >= C0;
+      const int cs = second ? C - C0 : C0, cl = second ? c - C0 : c;
+      const int slots = second ? p.gn_slots1 : p.gn_slots0;
+      const long long* sp = (second ? p.gn_stats1 : p.gn_stats0) + ((size_t)b * slots * cs + cl) * 2;
+      long long sa = 0, sd = 0;
+      for (int sl = 0; sl < slots; ++sl) {
+        const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(sp + (size_t)sl * cs * 2));
+        sa += v.x; sd += v.y;
+      }
+      // int64 -> float directly: one rounding, then an exact power-of-two scale - the same bits as going through double,
+      // without touching the FP64 pipe (measured: the first FP64 instruction of a kernel costs ~3 k cycles on this part)
+      fa = __ll2float_rn(sa) * (1.0f / 16777216.0f);
+      fd = __ll2float_rn(sd) * (1.0f / 16777216.0f);
+    };
+    if (live) {
+      float fa[KEEP], fd[KEEP];
+#pragma unroll
+      for (int q = 0; q < KEEP; ++q) {          // all loads of the first KEEP channels are in flight together
+        const int k = sub + q * TPG;
+        fa[q] = fd[q] = 0.f;
+        if (k < cg) {
+          const int c = g * cg + k;
+          gam[q] = __ldg(p.gn_gamma + c); bet[q] = __ldg(p.gn_beta + c);
+          chan_sums(c, fa[q], fd[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < KEEP; ++q) { a += fa[q]; d += fd[q]; }
+      for (int k = sub + KEEP * TPG; k < cg; k += TPG) {
+        float xa, xd;
+        chan_sums(g * cg + k, xa, xd);
+        a += xa; d += xd;
+      }
+    }
+#pragma unroll
+    for (int o = TPG >> 1; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if (live) {
+      const float inv_n = 1.0f / ((float)(p.H * p.W) * (float)cg);
+      const float mean = a * inv_n;
+      const float var = fmaxf(d * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float hs = do_swish ? 0.5f : 1.0f;
+      auto put = [&](int c, float gm, float bt) {
+        float2 v;
+        v.x = rstd * gm;
+        v.y = bt - mean * v.x;
+        v.x *= hs; v.y *= hs;
+        gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+      };
+#pragma unroll
+      for (int q = 0; q < KEEP; ++q) {
+        const int k = sub + q * TPG;
+        if (k < cg) put(g * cg + k, gam[q], bet[q]);
+      }
+      for (int k = sub + KEEP * TPG; k < cg; k += TPG) put(g * cg + k, __ldg(p.gn_gamma + g * cg + k), __ldg(p.gn_beta + g * cg + k));
+    }
+  } else if (p.gn) {
+    for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
+      const int im = idx / p.gn_C;
+      const int c = idx - im * p.gn_C;
+      float2 v = __ldg(p.gn + (size_t)min(b0 + im, p.B - 1) * p.gn_C + c);
+      if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
+      gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+    }
+  }
+  asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
 // CG = 2: two CTAs of a cluster (one TPC) run ONE M = 256 tile pair with tcgen05 cta_group::2. Each CTA loads its own
 // halo, transforms it, and drains its own 128 accumulator rows, but only HALF of every weight tile: the pair shares the
 // B operand, which halves the weight bytes through each CTA's shared-memory port and cuts the operand bytes a CTA feeds
@@ -286,31 +387,89 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  {
+    // Touch every 64-byte line of the kernel parameters at once: the constant cache starts cold at every launch, and the
+    // roles would otherwise take its misses one after the other (tile decode, segment list, GroupNorm fields, ...).
+    const int* pw = reinterpret_cast<const int*>(&p);
+    int touch = 0;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(ConvHaloParams) / 64); ++i) touch += pw[i * 16];
+    asm volatile("" ::"r"(touch));
+  }
+  const long long t_entry = p.dbg ? clock64() : 0;      // role timing: kernel entry on this SM (after the parameter touch)
 
+  // contiguous run of super tiles; order: x tile fastest, y tile, parity, image, n tile. (32-bit arithmetic: the host
+  // checks total_super * grid < 2^31; a 64-bit division is a ~500-cycle subroutine in front of the first TMA load.)
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;      // rank in the CTA pair; tile = 2 * super + rank
+  const int unit_id = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
+  const int sup_begin = (int)(((uint32_t)unit_id * (uint32_t)p.total_super) / (uint32_t)num_units);
+  const int sup_end = (int)(((uint32_t)(unit_id + 1) * (uint32_t)p.total_super) / (uint32_t)num_units);
+  struct Tile { int n_tile, x0, y0, b, par; };
+  // n / d and n % d for n < 2^22 through the host's float reciprocal (quotient off by at most one, then corrected): an
+  // integer division by a run-time value is ~150 cycles of dependent instructions, and a decode chains four of them in
+  // front of the first TMA load of every role
+  auto divmod = [](uint32_t n, uint32_t d, float inv, uint32_t& r) {
+    uint32_t q = __float2uint_rz(__uint2float_rn(n) * inv);
+    int rr = (int)(n - q * d);
+    if (rr < 0) { --q; rr += (int)d; } else if ((uint32_t)rr >= d) { ++q; rr -= (int)d; }
+    r = (uint32_t)rr;
+    return q;
+  };
+  auto decode = [&](int sup, int mt) {
+    uint32_t tile = (uint32_t)((sup * MT + mt) * CG) + crank, r;
+    Tile t;
+    tile = divmod(tile, (uint32_t)p.tiles_w, p.inv_tiles_w, r); t.x0 = (int)r * HALO_TW;
+    tile = divmod(tile, (uint32_t)p.tiles_h, p.inv_tiles_h, r); t.y0 = (int)r * HALO_TH;
+    tile = divmod(tile, (uint32_t)p.num_par, p.inv_num_par, r); t.par = (int)r;
+    tile = divmod(tile, (uint32_t)p.units, p.inv_units, r); t.b = (int)r * G::IMGS;
+    t.n_tile = (int)tile;
+    return t;
+  };
+
+  // ---- prologue. Each single-thread role initialises the barriers it produces into, so the two TMA producers can start
+  // loading before the CTA-wide rendezvous (they only ARRIVE on it): measured on B200, the first global access of a
+  // kernel takes ~3 k cycles (caches and TLBs start cold at every launch) and used to begin after ~2 k cycles of setup.
   if (warp == LW && lane == 0) {
     ptx::prefetch_tmap(&p.w_map);
     for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
     for (int i = 0; i < p.num_par; ++i) ptx::prefetch_tmap(&p.o_map[i]);
-  }
-  if (warp == LW + 1 && lane == 0) {
     for (int s = 0; s < AST; ++s) {
       ptx::mbar_init(a_full(s), 1);
       ptx::mbar_init(a_ready(s), CG == 2 ? 16 : 256);      // pair: one arrival per transform warp of both CTAs
       ptx::mbar_init(a_empty(s), 1);
     }
+    ptx::fence_barrier_init();
+  }
+  if (warp == LW + 1 && lane == 0) {
     for (int s = 0; s < WST; ++s) {
       ptx::mbar_init(w_full(s), 1);
       ptx::mbar_init(w_empty(s), 1);
     }
-    for (int b = 0; b < NBUF; ++b) {
-      ptx::mbar_init(tmem_full(b), 1);
-      ptx::mbar_init(tmem_empty(b), CG == 2 ? 8 : 128 * ESETS);   // pair: one arrival per epilogue warp of both CTAs
-    }
     ptx::fence_barrier_init();
   }
   if (warp == LW + 2) {
+    if (lane == 0) {
+      for (int b = 0; b < NBUF; ++b) {
+        ptx::mbar_init(tmem_full(b), 1);
+        ptx::mbar_init(tmem_empty(b), CG == 2 ? 8 : 128 * ESETS);   // pair: one arrival per epilogue warp of both CTAs
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
     if (CG == 2) tmem_alloc_pair(tmem_slot, NBUF * MT * BLOCK_N);
     else ptx::tmem_alloc(tmem_slot, NBUF * MT * BLOCK_N);
+  }
+  // Transform warps build the first image's GroupNorm table NOW, before the CTA-wide rendezvous and before the TMA
+  // producers queue the first halo and weight tiles of all 148 CTAs: measured on B200, a global load issued once that
+  // burst is in flight takes ~3 k cycles instead of ~1 k, and the table sat on the path to the first MMA. (Not under
+  // programmatic dependent launch: the statistics may not be final before griddepcontrol.wait.)
+  int tab_b_early = -1;
+  if (FUSE_GN && CG == 1 && !p.pdl && (warp < 4 || (warp >= 8 && warp < 12)) && sup_begin < sup_end) {
+    const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;
+    tab_b_early = decode(sup_begin, 0).b;
+    halo_build_gn_table<G::IMGS>(p, reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET), p.gn_C + 2 * (p.gn_C >> 3), tt,
+                                 tab_b_early, p.gn_swish != 0);
+    if (p.dbg && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
   }
   if (GEO == 2) {
     // pixels 125 .. 134 of every stage: the zero row below the last image (TMA never writes them, nobody else does)
@@ -321,32 +480,24 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     fence_proxy_async_smem();
   }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them
-  ptx::tc_fence_after();
+  if (CG == 2) {
+    ptx::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them
+    ptx::tc_fence_after();
+  } else if (warp == LW || warp == LW + 1) {
+    asm volatile("bar.arrive 3, %0;" ::"n"(halo_threads(BLOCK_N)) : "memory");      // producers do not wait
+  } else {
+    ptx::tc_fence_before();
+    asm volatile("bar.sync 3, %0;" ::"n"(halo_threads(BLOCK_N)) : "memory");
+    ptx::tc_fence_after();
+  }
   // Everything above overlapped the previous kernel's tail (programmatic dependent launch); its results are needed from
   // here on - except by the weight producer, which only reads constants and starts filling its ring at once.
-  if (warp != LW + 1) pdl_wait();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  // contiguous run of super tiles; order: x tile fastest, y tile, parity, image, n tile
-  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;      // rank in the CTA pair; tile = 2 * super + rank
-  const int unit_id = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
-  const int sup_begin = (int)(((long long)unit_id * p.total_super) / num_units);
-  const int sup_end = (int)(((long long)(unit_id + 1) * p.total_super) / num_units);
-  struct Tile { int n_tile, x0, y0, b, par; };
-  auto decode = [&](int sup, int mt) {
-    int tile = (sup * MT + mt) * CG + (int)crank;
-    Tile t;
-    t.x0 = (tile % p.tiles_w) * HALO_TW; tile /= p.tiles_w;
-    t.y0 = (tile % p.tiles_h) * HALO_TH; tile /= p.tiles_h;
-    t.par = tile % p.num_par; tile /= p.num_par;
-    t.b = (tile % p.units) * G::IMGS;
-    t.n_tile = tile / p.units;
-    return t;
-  };
+  if (p.pdl && warp != LW + 1) pdl_wait();
+  uint32_t tmem_base = 0;
+  if (CG == 2 || (warp != LW && warp != LW + 1)) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 15] = (unsigned long long)(clock64() - t_entry);   // [15] prologue
 
   if (warp == LW) {
     if (ptx::elect_one()) {
@@ -388,7 +539,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   } else if (warp == LW + 1) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- weight producer
+      // The ring is NOT filled at once: a full ring is 100-400 KB per SM queued in front of the first halo tile and of
+      // the GroupNorm statistics (measured: every other first access of the kernel then takes ~3 k cycles instead of
+      // ~1 k). Two stages go out, the rest follows once the first halo tile has landed (a_full(0), phase 0 - a
+      // non-consuming wait; its second completion needs MMAs that need more than two weight stages, so it cannot pass us).
       int ws = 0; uint32_t wphase = 0;
+      int early = CG == 1 ? 2 : -1;
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         const Tile t = decode(sup, 0);
         const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N + (int)crank * (BLOCK_N / CG);
@@ -396,6 +552,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           const HaloSeg seg = p.seg[sg];
           for (int cb = 0; cb < seg.cblocks; ++cb) {
             for (int tap = 0; tap < seg.ntaps; ++tap) {
+              if (early == 0) ptx::mbar_wait(a_full(0), 0u);
+              if (early >= 0) --early;
               ptx::mbar_wait(w_empty(ws), wphase ^ 1u);
               if (CG == 2) {
                 // both halves of the tile complete on the LEADER's barrier, which the leader arms for both
@@ -433,6 +591,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       bool ready = false;
       int it = 0;
       HDBG_DECL();
+      long long t_first_mma = 0;
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
@@ -460,6 +619,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                 HDBG_ACC(1);
               }
               ptx::tc_fence_after();
+              if (p.dbg && t_first_mma == 0) t_first_mma = clock64();
               const uint32_t b_lo = w_lo0 + (uint32_t)ws * (uint32_t)(S::W_STAGE >> 4);
               const uint32_t wcur = w_empty(ws);
               if (++ws == WST) { ws = 0; wphase ^= 1u; }
@@ -491,6 +651,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       // be scheduled (they run their prologue and block in pdl_wait until this grid has completed)
       pdl_launch_dependents();
       HDBG_FLUSH(4, 3);      // [4] MMA waits A ready, [5] waits W full, [6] waits TMEM empty
+      if (p.dbg) {           // [12] kernel entry -> first MMA issued ("fill"), [13] entry -> last MMA issued
+        p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(t_first_mma - t_entry);
+        p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)(clock64() - t_entry);
+      }
     }
   } else if (BLOCK_N == 16 && warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ tail epilogue: sampler update
@@ -720,9 +884,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         if (sup + 1 == sup_end || (sup + 1) / p.seg_len_super != seg) {
           // the CTA's run over this (n tile, image) segment ends: publish its partial sums. The four
           // warps' sums meet in the (drained) staging slabs: [column][sum|sq] int64 per warp.
-          const long long GU = num_units, T = p.total_super;
-          const int first_unit = (int)((((long long)seg * p.seg_len_super + 1) * GU - 1) / T);
-          const int last_unit = (int)((((long long)(seg + 1) * p.seg_len_super) * GU - 1) / T);
+          const uint32_t GU = (uint32_t)num_units, T = (uint32_t)p.total_super;
+          const int first_unit = (int)((((uint32_t)seg * (uint32_t)p.seg_len_super + 1u) * GU - 1u) / T);
+          const int last_unit = (int)((((uint32_t)(seg + 1) * (uint32_t)p.seg_len_super) * GU - 1u) / T);
           const int slot = (unit_id - first_unit) * CG + (int)crank;       // a pair publishes two slots
           const bool is_last = unit_id == last_unit && (int)crank == CG - 1;
           if (lane == 0) bulk_wait_read<0>();
@@ -765,6 +929,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
+    if (tid_e == 0 && p.dbg) p.dbg[blockIdx.x * 16 + 14] = (unsigned long long)(clock64() - t_entry);   // [14] entry -> epilogue done
 #undef HALO_EPI_SYNC
   } else if (XF && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
@@ -779,73 +944,17 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const bool do_swish = p.gn_swish != 0;
     float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C (padded)], halved if swish
     const int gn_pitch = p.gn_C + 2 * (p.gn_C >> 3);
-    int tab_b = -1;
+    int tab_b = tab_b_early;
     int as = 0; uint32_t aphase = 0;
+    bool first_halo_seen = false;
+    if (p.dbg && tt == 0) p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry);   // [7] transform role entered
     HDBG_DECL();
     for (int sup = sup_begin; sup < sup_end; ++sup) {
       Tile t[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
       if (FUSE_GN && t[0].b != tab_b) {
-        asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous table
-        if (p.gn_stats0) {
-          // (1) per-channel (sum, sum of squares): exact int64 sum over the producer's slots, then to float
-          const int C = p.gn_C, C0 = p.gn_C0;
-          for (int idx = tt; idx < IMGS * C; idx += 256) {
-            const int im = idx / C;
-            const int c = idx - im * C;
-            const int b = min(t[0].b + im, p.B - 1);
-            const bool second = c >= C0;
-            const int cs = second ? C - C0 : C0, cl = second ? c - C0 : c;
-            const int slots = second ? p.gn_slots1 : p.gn_slots0;
-            const long long* sp = (second ? p.gn_stats1 : p.gn_stats0) + ((size_t)b * slots * cs + cl) * 2;
-            long long a = 0, d = 0;
-            for (int k = 0; k < slots; ++k) {
-              const longlong2 v = *reinterpret_cast<const longlong2*>(sp + (size_t)k * cs * 2);
-              a += v.x; d += v.y;
-            }
-            gtab[im * gn_pitch + c + 2 * (c >> 3)] =
-                make_float2((float)((double)a * STAT_FIXED_INV), (float)((double)d * STAT_FIXED_INV));
-          }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          // (2) per-group mean and 1/std (groups may straddle the seam of a concat, hence per-channel sums)
-          float2* gstat = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET + S::GSTAT_OFFSET_IN_GN);
-          const int cg = C / p.gn_groups;
-          if (tt < IMGS * p.gn_groups) {
-            const int im = tt / p.gn_groups, g = tt - im * p.gn_groups;
-            float a = 0.f, d = 0.f;
-            for (int k = 0; k < cg; ++k) {
-              const int c = g * cg + k;
-              const float2 v = gtab[im * gn_pitch + c + 2 * (c >> 3)];
-              a += v.x; d += v.y;
-            }
-            const float inv_n = 1.0f / ((float)(p.H * p.W) * (float)cg);
-            const float mean = a * inv_n;
-            const float var = fmaxf(d * inv_n - mean * mean, 0.f);
-            gstat[tt] = make_float2(mean, rsqrtf(var + 1e-5f));
-          }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          // (3) (scale, shift) = (rstd * gamma, beta - mean * rstd * gamma), pre-halved for the tanh form of Swish
-          for (int idx = tt; idx < IMGS * C; idx += 256) {
-            const int im = idx / C;
-            const int c = idx - im * C;
-            const float2 ms = gstat[im * p.gn_groups + c / cg];
-            float2 v;
-            v.x = ms.y * __ldg(p.gn_gamma + c);
-            v.y = __ldg(p.gn_beta + c) - ms.x * v.x;
-            if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
-            gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
-          }
-        } else if (p.gn) {
-          for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
-            const int im = idx / p.gn_C;
-            const int c = idx - im * p.gn_C;
-            float2 v = __ldg(p.gn + (size_t)min(t[0].b + im, p.B - 1) * p.gn_C + c);
-            if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
-            gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;       // 10 float2 slots per 8 channels
-          }
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        halo_build_gn_table<G::IMGS>(p, gtab, gn_pitch, tt, t[0].b, do_swish);
         tab_b = t[0].b;
       }
       for (int sg = 0; sg < p.num_segs; ++sg) {
@@ -868,6 +977,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           }
           ptx::mbar_wait(a_full(as), aphase);
           HDBG_ACC(0);
+          if (p.dbg && tt == 0 && !first_halo_seen) { first_halo_seen = true; p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry); }   // [7] first halo landed
           HDBG_T0();
           if (seg.gn_off >= 0 && !(p.ablate & 2)) {
 #pragma unroll
