@@ -276,39 +276,55 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
     float a = 0.f, d = 0.f, gam[KEEP], bet[KEEP];
 #pragma unroll
     for (int q = 0; q < KEEP; ++q) gam[q] = bet[q] = 0.f;
-    auto chan_sums = [&](int c, float& fa, float& fd) {
+    // statistics of channel c: pointer to slot 0 of image b, slot count and slot stride (in int64 units)
+    auto chan_ptr = [&](int c, int& slots, int& stride) {
       const bool second = c >= C0;
       const int cs = second ? C - C0 : C0, cl = second ? c - C0 : c;
-      const int slots = second ? p.gn_slots1 : p.gn_slots0;
-      const long long* sp = (second ? p.gn_stats1 : p.gn_stats0) + ((size_t)b * slots * cs + cl) * 2;
-      long long sa = 0, sd = 0;
-      for (int sl = 0; sl < slots; ++sl) {
-        const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(sp + (size_t)sl * cs * 2));
-        sa += v.x; sd += v.y;
+      slots = second ? p.gn_slots1 : p.gn_slots0;
+      stride = cs * 2;
+      return (second ? p.gn_stats1 : p.gn_stats0) + ((size_t)b * slots * cs + cl) * 2;
+    };
+    auto finish = [&](longlong2 v, const long long* sp, int slots, int stride, float& fa, float& fd) {
+      long long sa = v.x, sd = v.y;
+#pragma unroll 1      // slots beyond the first (rare, 1-3): a rolled loop - unrolled 16-way it put ~500 instructions here
+      for (int sl = 1; sl < slots; ++sl) {
+        sp += stride;
+        const longlong2 w = __ldcg(reinterpret_cast<const longlong2*>(sp));
+        sa += w.x; sd += w.y;
       }
-      // int64 -> float directly: one rounding, then an exact power-of-two scale - the same bits as going through double,
-      // without touching the FP64 pipe (measured: the first FP64 instruction of a kernel costs ~3 k cycles on this part)
+      // int64 -> float directly: one rounding, then an exact power-of-two scale (the same bits as going through double)
       fa = __ll2float_rn(sa) * (1.0f / 16777216.0f);
       fd = __ll2float_rn(sd) * (1.0f / 16777216.0f);
     };
     if (live) {
-      float fa[KEEP], fd[KEEP];
+      longlong2 v0[KEEP];
+      const long long* sp[KEEP];
+      int nsl[KEEP], str[KEEP];
 #pragma unroll
-      for (int q = 0; q < KEEP; ++q) {          // all loads of the first KEEP channels are in flight together
+      for (int q = 0; q < KEEP; ++q) {          // slot 0, gamma and beta of the first KEEP channels: all in flight together
         const int k = sub + q * TPG;
-        fa[q] = fd[q] = 0.f;
+        v0[q] = make_longlong2(0, 0); sp[q] = nullptr; nsl[q] = 0; str[q] = 0;
         if (k < cg) {
           const int c = g * cg + k;
+          sp[q] = chan_ptr(c, nsl[q], str[q]);
+          v0[q] = __ldcg(reinterpret_cast<const longlong2*>(sp[q]));
           gam[q] = __ldg(p.gn_gamma + c); bet[q] = __ldg(p.gn_beta + c);
-          chan_sums(c, fa[q], fd[q]);
         }
       }
 #pragma unroll
-      for (int q = 0; q < KEEP; ++q) { a += fa[q]; d += fd[q]; }
+      for (int q = 0; q < KEEP; ++q) {
+        if (sub + q * TPG < cg) {
+          float fa, fd;
+          finish(v0[q], sp[q], nsl[q], str[q], fa, fd);
+          a += fa; d += fd;
+        }
+      }
       for (int k = sub + KEEP * TPG; k < cg; k += TPG) {
-        float xa, xd;
-        chan_sums(g * cg + k, xa, xd);
-        a += xa; d += xd;
+        int ns, st;
+        const long long* ptr = chan_ptr(g * cg + k, ns, st);
+        float fa, fd;
+        finish(__ldcg(reinterpret_cast<const longlong2*>(ptr)), ptr, ns, st, fa, fd);
+        a += fa; d += fd;
       }
     }
 #pragma unroll
@@ -429,17 +445,49 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   // ---- prologue. Each single-thread role initialises the barriers it produces into, so the two TMA producers can start
   // loading before the CTA-wide rendezvous (they only ARRIVE on it): measured on B200, the first global access of a
   // kernel takes ~3 k cycles (caches and TLBs start cold at every launch) and used to begin after ~2 k cycles of setup.
-  if (warp == LW && lane == 0) {
-    ptx::prefetch_tmap(&p.w_map);
-    for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
-    for (int i = 0; i < p.num_par; ++i) ptx::prefetch_tmap(&p.o_map[i]);
-    for (int s = 0; s < AST; ++s) {
-      ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_ready(s), CG == 2 ? 16 : 256);      // pair: one arrival per transform warp of both CTAs
-      ptx::mbar_init(a_empty(s), 1);
+  // One halo stage = the MT tiles' boxes of one 64-channel block, all completing on a_full(stage).
+  auto issue_halo = [&](int stage, int map, int cb, const Tile* t) {
+    ptx::mbar_expect_tx(a_full(stage), (p.ablate & 8) ? 0 : MT * G::BYTES);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (p.ablate & 8) break;
+      if (GEO == 0)
+        ptx::tma_load_4d(smem_base + stage * S::A_STAGE + m * G::STRIDE, &p.a_map[map], a_full(stage),
+                         cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
+      else if (GEO == 2)      // natural (C, W, H, B) order: the 5 x 5 grids of five images, end to end
+        ptx::tma_load_4d(smem_base + stage * S::A_STAGE + m * G::STRIDE + G::TMA_OFF, &p.a_map[map], a_full(stage),
+                         cb * CONV_BLOCK_K, -1, -1, t[m].b);
+      else      // view ordered (C, W, B, H): both images of the pair in one box
+        ptx::tma_load_4d(smem_base + stage * S::A_STAGE + m * G::STRIDE, &p.a_map[map], a_full(stage),
+                         cb * CONV_BLOCK_K, -1, t[m].b, -1);
     }
-    ptx::fence_barrier_init();
+  };
+  // The first halo tile is on the path to the first MMA (it lands ~3.5 k cycles after it is requested, then has to be
+  // transformed): the producer thread requests it before anything else - its own barriers, one decode, one TMA.
+  bool halo0_issued = false;
+  if (warp == LW) {
+    halo0_issued = CG == 1 && !p.pdl && sup_begin < sup_end;      // uniform over the warp
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.a_map[p.seg[0].map]);
+      for (int s = 0; s < AST; ++s) {
+        ptx::mbar_init(a_full(s), 1);
+        ptx::mbar_init(a_ready(s), CG == 2 ? 16 : 256);      // pair: one arrival per transform warp of both CTAs
+        ptx::mbar_init(a_empty(s), 1);
+      }
+      ptx::fence_barrier_init();
+      if (halo0_issued) {
+        Tile t[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) t[m] = decode(sup_begin, m);
+        issue_halo(0, p.seg[0].map, 0, t);
+      }
+      for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
+    }
+    __syncwarp();
   }
+  if (warp == LW + 1 && lane == 0) ptx::prefetch_tmap(&p.w_map);
+  if (warp == 4 && lane == 0)
+    for (int i = 0; i < p.num_par; ++i) ptx::prefetch_tmap(&p.o_map[i]);
   if (warp == LW + 1 && lane == 0) {
     for (int s = 0; s < WST; ++s) {
       ptx::mbar_init(w_full(s), 1);
@@ -512,22 +560,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const HaloSeg seg = p.seg[sg];
           for (int cb = 0; cb < seg.cblocks; ++cb) {
-            HDBG_T0();
-            ptx::mbar_wait(a_empty(as), aphase ^ 1u);
-            HDBG_ACC(0);
-            ptx::mbar_expect_tx(a_full(as), (p.ablate & 8) ? 0 : MT * G::BYTES);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              if (p.ablate & 8) break;
-              if (GEO == 0)
-                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
-                                 cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
-              else if (GEO == 2)      // natural (C, W, H, B) order: the 5 x 5 grids of five images, end to end
-                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE + G::TMA_OFF, &p.a_map[seg.map], a_full(as),
-                                 cb * CONV_BLOCK_K, -1, -1, t[m].b);
-              else      // view ordered (C, W, B, H): both images of the pair in one box
-                ptx::tma_load_4d(smem_base + as * S::A_STAGE + m * G::STRIDE, &p.a_map[seg.map], a_full(as),
-                                 cb * CONV_BLOCK_K, -1, t[m].b, -1);
+            if (!(halo0_issued && sup == sup_begin && sg == 0 && cb == 0)) {      // (that one went out in the prologue)
+              HDBG_T0();
+              ptx::mbar_wait(a_empty(as), aphase ^ 1u);
+              HDBG_ACC(0);
+              issue_halo(as, seg.map, cb, t);
             }
             if (++as == AST) { as = 0; aphase ^= 1u; }
           }
