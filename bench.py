@@ -248,8 +248,19 @@ def main():
     conv_share = conv_ms / step_ms
     achieved = conv_flops / (graph_step_ms * conv_share * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    traffic, traffic_note = None, None
+    try:      # DRAM bytes of the dominant kernel class from the committed `ncu --set full` capture (per launch)
+        with open(os.path.join(ROOT, "profiles", "r01f_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = (f"{tj['kernel']}: {tj['dram_bytes_per_launch'] / 1e6:.1f} MB DRAM per launch against "
+                        f"{tj['algorithmic_bytes_per_launch'] / 1e6:.1f} MB algorithmic ({tj['source']}); "
+                        "`achieved` above aggregates all 66 conv launches of a step")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_umma_kernel (all tcgen05 conv launches of one sampling step)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a long step)",
                 "launches_per_step": len(conv), "flops_per_step": conv_flops,
                 "conv_ms_per_step": graph_step_ms * conv_share, "conv_share_of_step": conv_share,

@@ -98,3 +98,23 @@ def test_product_synthetic_generator_matches_oracle_copy():
     c1, n1 = synthetic.inputs(2, 16, 3, seed=5)
     c2, n2 = make_inputs(2, 16, 3, seed=5)
     assert torch.equal(c1, c2) and torch.equal(n1, n2)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import, open or exec it."""
+    import os
+    import re
+    from conftest import PKG
+    bad = []
+    for root, _, files in os.walk(PKG):
+        if os.sep + "build" in root:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|oracle\.", text, flags=re.M) and "oracle" in text:
+                    # comments that merely NAME the oracle as the checker are fine; imports / paths are not
+                    for line in text.splitlines():
+                        if re.search(r"^\s*(from|import)\s+oracle\b", line) or re.search(r"[\"']\S*oracle/", line):
+                            bad.append((f, line.strip()))
+    assert not bad, bad
