@@ -420,7 +420,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   const int unit_id = (int)blockIdx.x / CG, num_units = (int)gridDim.x / CG;
   const int sup_begin = (int)(((uint32_t)unit_id * (uint32_t)p.total_super) / (uint32_t)num_units);
   const int sup_end = (int)(((uint32_t)(unit_id + 1) * (uint32_t)p.total_super) / (uint32_t)num_units);
-  struct Tile { int n_tile, x0, y0, b, par; };
+  struct Tile { int n_tile, x0, y0, b, par, unit; };
   // n / d and n % d for n < 2^22 through the host's float reciprocal (quotient off by at most one, then corrected): an
   // integer division by a run-time value is ~150 cycles of dependent instructions, and a decode chains four of them in
   // front of the first TMA load of every role
@@ -437,9 +437,27 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     tile = divmod(tile, (uint32_t)p.tiles_w, p.inv_tiles_w, r); t.x0 = (int)r * HALO_TW;
     tile = divmod(tile, (uint32_t)p.tiles_h, p.inv_tiles_h, r); t.y0 = (int)r * HALO_TH;
     tile = divmod(tile, (uint32_t)p.num_par, p.inv_num_par, r); t.par = (int)r;
-    tile = divmod(tile, (uint32_t)p.units, p.inv_units, r); t.b = (int)r * G::IMGS;
+    tile = divmod(tile, (uint32_t)p.units, p.inv_units, r); t.b = (int)r * G::IMGS; t.unit = (int)r;
     t.n_tile = (int)tile;
     return t;
+  };
+  // Every role walks the same tile sequence; after the first decode the walk is carried forward with compares instead of
+  // being decoded again (a decode is ~80 dependent instructions, and the epilogue ran three of them per super tile).
+  auto tile_next = [&](Tile& t) {
+#pragma unroll
+    for (int s = 0; s < CG; ++s) {
+      t.x0 += HALO_TW;
+      if (t.x0 == p.tiles_w * HALO_TW) {
+        t.x0 = 0; t.y0 += HALO_TH;
+        if (t.y0 == p.tiles_h * HALO_TH) {
+          t.y0 = 0;
+          if (++t.par == p.num_par) {
+            t.par = 0; t.b += G::IMGS;
+            if (++t.unit == p.units) { t.unit = 0; t.b = 0; ++t.n_tile; }
+          }
+        }
+      }
+    }
   };
 
   // ---- prologue. Each single-thread role initialises the barriers it produces into, so the two TMA producers can start
@@ -553,10 +571,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int as = 0; uint32_t aphase = 0;
       HDBG_DECL();
       const long long hd_start = p.dbg ? clock64() : 0;
+      Tile walk = decode(sup_begin, 0);
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         Tile t[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
+        for (int m = 0; m < MT; ++m) { t[m] = walk; tile_next(walk); }
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const HaloSeg seg = p.seg[sg];
           for (int cb = 0; cb < seg.cblocks; ++cb) {
@@ -582,8 +601,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       // non-consuming wait; its second completion needs MMAs that need more than two weight stages, so it cannot pass us).
       int ws = 0; uint32_t wphase = 0;
       int early = CG == 1 ? 2 : -1;
+      Tile walk = decode(sup_begin, 0);
       for (int sup = sup_begin; sup < sup_end; ++sup) {
-        const Tile t = decode(sup, 0);
+        const Tile t = walk;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tile_next(walk);
         const int wrow = t.par * p.Cout + t.n_tile * BLOCK_N + (int)crank * (BLOCK_N / CG);
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const HaloSeg seg = p.seg[sg];
@@ -629,10 +651,13 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int it = 0;
       HDBG_DECL();
       long long t_first_mma = 0;
+      Tile walk = decode(sup_begin, 0);
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
-        const int par = decode(sup, 0).par;
+        const int par = walk.par;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tile_next(walk);
         HDBG_T0();
         ptx::mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);
         HDBG_ACC(2);
@@ -709,6 +734,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     int it = 0;
     HDBG_DECL();
+    Tile walk = decode(sup_begin, 0);
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -718,7 +744,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const Tile t = decode(sup, m);
+        const Tile t = walk;
+        tile_next(walk);
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N), v);
         ptx::tmem_ld_wait();
@@ -801,6 +828,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
     int it = 0, stg = 0;
     HDBG_DECL();
+    Tile walk = decode(sup_begin, 0);
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -808,11 +836,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       ptx::mbar_wait(tmem_full(buf), use & 1u);
       HDBG_ACC(0);
       ptx::tc_fence_after();
-      const Tile t0 = decode(sup, 0);
+      const Tile t0 = walk;
       const int n0 = t0.n_tile * BLOCK_N;
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const Tile t = decode(sup, m);
+        const Tile t = walk;
+        tile_next(walk);      // after the loop: the first tile of the next super tile
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N);
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
@@ -917,8 +946,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
 
       if (do_stats) {
-        const int seg = sup / p.seg_len_super;
-        if (sup + 1 == sup_end || (sup + 1) / p.seg_len_super != seg) {
+        const int seg = t0.n_tile * p.units + t0.unit;      // = sup / seg_len_super: a segment is one (n tile, unit)
+        if (sup + 1 == sup_end || walk.unit != t0.unit || walk.n_tile != t0.n_tile) {
           // the CTA's run over this (n tile, image) segment ends: publish its partial sums. The four
           // warps' sums meet in the (drained) staging slabs: [column][sum|sq] int64 per warp.
           const uint32_t GU = (uint32_t)num_units, T = (uint32_t)p.total_super;
@@ -984,12 +1013,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     int tab_b = tab_b_early;
     int as = 0; uint32_t aphase = 0;
     bool first_halo_seen = false;
-    if (p.dbg && tt == 0) p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry);   // [7] transform role entered
     HDBG_DECL();
+    Tile walk = decode(sup_begin, 0);
     for (int sup = sup_begin; sup < sup_end; ++sup) {
       Tile t[MT];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) t[m] = decode(sup, m);
+      for (int m = 0; m < MT; ++m) { t[m] = walk; tile_next(walk); }
       if (FUSE_GN && t[0].b != tab_b) {
         halo_build_gn_table<G::IMGS>(p, gtab, gn_pitch, tt, t[0].b, do_swish);
         tab_b = t[0].b;
