@@ -23,6 +23,7 @@ void conv_halo_init_device() {
   set_attr<64, 1, false>();  set_attr<64, 1, true>();
   set_attr<64, 2, false>();  set_attr<64, 2, true>();
   set_attr<128, 1, false>(); set_attr<128, 1, true>();
+  set_attr<128, 2, false>(); set_attr<128, 2, true>();
   set_attr<256, 1, false>(); set_attr<256, 1, true>();
   set_attr<16, 1, false>();  set_attr<16, 1, true>();
   set_attr<16, 2, false>();  set_attr<16, 2, true>();
@@ -237,9 +238,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     double best = 1e30;
     int fcg = 0;
     if (const char* e = getenv("B200SR3_HALO_CG")) fcg = atoi(e);
+    static const bool allow_128x2 = [] { const char* e = getenv("B200SR3_HALO_128X2"); return e && e[0] == '1'; }();
     int cg_min_bn = 64;
     if (const char* e = getenv("B200SR3_HALO_CG_MIN_BN")) cg_min_bn = atoi(e);
-    const int cand[9][3] = {{256, 1, 2}, {128, 1, 2}, {64, 1, 2}, {256, 1, 1}, {128, 1, 1}, {64, 2, 1}, {64, 1, 1}, {16, 2, 1}, {16, 1, 1}};
+    const int cand[10][3] = {{256, 1, 2}, {128, 1, 2}, {64, 1, 2}, {256, 1, 1}, {128, 2, 1}, {128, 1, 1}, {64, 2, 1}, {64, 1, 1}, {16, 2, 1}, {16, 1, 1}};
     // CTA pairs are opt-in (B200SR3_HALO_CG=2, optionally only for BLOCK_N >= B200SR3_HALO_CG_MIN_BN): in burst timing
     // they are 0-60 % SLOWER than the one-CTA shapes on every layer of the R=128 UNet
     // (profiles/r01e_cta_pair_halo_bench.txt) - the pair runs in lock step through cross-CTA barriers and gives up the
@@ -252,6 +254,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (g2 && c[0] != 64) continue;
+      if (c[0] == 128 && c[1] == 2 && !allow_128x2) continue;
       if (out.C % c[0] != 0 || tiles_img % c[1] != 0) continue;
       const int tiles_per_super = c[1] * c[2];
       if ((fbn && c[0] != fbn) || (fmt && c[1] != fmt)) continue;
@@ -316,6 +319,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     else if (g1 && bn == 128) launch_halo<128, 1, 1>(*pp, any_gn, grid, s);
     else if (g1) launch_halo<64, 1, 1>(*pp, any_gn, grid, s);
     else if (bn == 256) launch_halo<256, 1>(*pp, any_gn, grid, s);
+    else if (bn == 128 && mt == 2) launch_halo<128, 2>(*pp, any_gn, grid, s);
     else if (bn == 128) launch_halo<128, 1>(*pp, any_gn, grid, s);
     else if (bn == 64 && mt == 2) launch_halo<64, 2>(*pp, any_gn, grid, s);
     else if (bn == 64) launch_halo<64, 1>(*pp, any_gn, grid, s);

@@ -38,7 +38,7 @@ CASES = [
     (4, 128, 0, 0, 0, 4, 4, 128, 0, 1),             # folded upsample 4 -> 8
     (11, 64, 0, 64, 0, 4, 4, 64, 1, 0),             # three tiles, the last one holds a single image
 ]
-SHAPES = [(0, 0), (64, 1), (64, 2), (128, 1), (256, 1)]
+SHAPES = [(0, 0), (64, 1), (64, 2), (128, 1), (128, 2), (256, 1)]
 
 
 def _block(x0, x1, gamma, beta, w, b, r0, r1, wres, up, want_stats=True, iters=0):
