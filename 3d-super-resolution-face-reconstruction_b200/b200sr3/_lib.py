@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sr3.so")
+# B200SR3_LIB selects another build of the same library (same-box A/B runs of two kernel variants)
+LIB_PATH = os.environ.get("B200SR3_LIB") or os.path.join(_HERE, "libb200sr3.so")
 MAX_LEVELS = 8
 NOISE_INJECTED = 1
 NOISE_PHILOX = 2

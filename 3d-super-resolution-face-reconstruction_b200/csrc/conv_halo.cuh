@@ -651,6 +651,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int it = 0;
       HDBG_DECL();
       long long t_first_mma = 0;
+      const bool dbg_on = p.dbg != nullptr;
+      uint32_t b_cur = w_lo0, w_full_cur = w_full(0), w_empty_cur = w_empty(0);      // running per-stage values of ws
       Tile walk = decode(sup_begin, 0);
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
         const int buf = it & 1;
@@ -674,18 +676,21 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             HDBG_ACC(0);
             uint32_t a_lo = a_lo0 + (uint32_t)as * (uint32_t)(S::A_STAGE >> 4) + pix0 * 8u;
             int tx = 0;
+            if (dbg_on && t_first_mma == 0) t_first_mma = clock64();
+            // The tap loop is THE critical instruction stream of the Cout = 64 layers: eight 48-cycle MMAs per tap leave
+            // ~380 cycles, and one thread retires ~5 cycles per dependent instruction. Everything that is not an MMA is
+            // kept to running pointers (no multiplications, no parameter reloads, no timing code).
             for (int tap = 0; tap < ntaps; ++tap) {
               if (!ready) {
-                HDBG_T0();
-                ptx::mbar_wait(w_full(ws), wphase);
-                HDBG_ACC(1);
+                if (dbg_on) { HDBG_T0(); ptx::mbar_wait(w_full_cur, wphase); HDBG_ACC(1); }
+                else ptx::mbar_wait(w_full_cur, wphase);
               }
               ptx::tc_fence_after();
-              if (p.dbg && t_first_mma == 0) t_first_mma = clock64();
-              const uint32_t b_lo = w_lo0 + (uint32_t)ws * (uint32_t)(S::W_STAGE >> 4);
-              const uint32_t wcur = w_empty(ws);
-              if (++ws == WST) { ws = 0; wphase ^= 1u; }
-              ready = ptx::mbar_test_wait(w_full(ws), wphase);      // look one stage ahead
+              const uint32_t b_lo = b_cur;
+              const uint32_t wcur = w_empty_cur;
+              b_cur += (uint32_t)(S::W_STAGE >> 4); w_full_cur += 8u; w_empty_cur += 8u;
+              if (++ws == WST) { ws = 0; wphase ^= 1u; b_cur = w_lo0; w_full_cur = w_full(0); w_empty_cur = w_empty(0); }
+              ready = ptx::mbar_test_wait(w_full_cur, wphase);      // look one stage ahead
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
 #pragma unroll

@@ -132,8 +132,9 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trap (-> cudaErrorLaunchFailure), never as a
 // hung GPU. ~2 s at 2 GHz.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// The spinning part lives out of line: inlined, its clock arithmetic, printf and trap sat in the middle of every hot loop
+// (~30 instructions per wait site, most painfully in the single-thread MMA issue loop).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 100000u)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -142,6 +143,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // One lane of a fully converged warp. Unlike `lane == 0`, the compiler knows exactly one thread is
 // active under this predicate, so tcgen05 / TMA operands stay in uniform registers (no per-lane

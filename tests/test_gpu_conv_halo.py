@@ -117,10 +117,11 @@ def test_every_tile_shape(shape):
     args = _make(case, seed=5)
     ref = _reference(*args)
     cu = [a.cuda() if torch.is_tensor(a) else a for a in args]
-    old = {k: os.environ.get(k) for k in ("B200SR3_HALO_BN", "B200SR3_HALO_MT")}
+    old = {k: os.environ.get(k) for k in ("B200SR3_HALO_BN", "B200SR3_HALO_MT", "B200SR3_HALO_128X2")}
     try:
         if shape[0]:
             os.environ["B200SR3_HALO_BN"], os.environ["B200SR3_HALO_MT"] = str(shape[0]), str(shape[1])
+            os.environ["B200SR3_HALO_128X2"] = "1"          # the (128, 2) shape is opt-in
         y, st, _ = _block(*cu)
     finally:
         for k, v in old.items():
