@@ -460,6 +460,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
   };
 
+  const Tile tile0 = decode(sup_begin, 0);      // decoded once; every role starts its walk from it
+
   // ---- prologue. Each single-thread role initialises the barriers it produces into, so the two TMA producers can start
   // loading before the CTA-wide rendezvous (they only ARRIVE on it): measured on B200, the first global access of a
   // kernel takes ~3 k cycles (caches and TLBs start cold at every launch) and used to begin after ~2 k cycles of setup.
@@ -496,7 +498,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (halo0_issued) {
         Tile t[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) t[m] = decode(sup_begin, m);
+        Tile w0 = tile0;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { t[m] = w0; tile_next(w0); }
         issue_halo(0, p.seg[0].map, 0, t);
       }
       for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
@@ -532,7 +536,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   int tab_b_early = -1;
   if (FUSE_GN && CG == 1 && !p.pdl && (warp < 4 || (warp >= 8 && warp < 12)) && sup_begin < sup_end) {
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;
-    tab_b_early = decode(sup_begin, 0).b;
+    tab_b_early = tile0.b;
     halo_build_gn_table<G::IMGS>(p, reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET), p.gn_C + 2 * (p.gn_C >> 3), tt,
                                  tab_b_early, p.gn_swish != 0);
     if (p.dbg && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
@@ -571,7 +575,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int as = 0; uint32_t aphase = 0;
       HDBG_DECL();
       const long long hd_start = p.dbg ? clock64() : 0;
-      Tile walk = decode(sup_begin, 0);
+      Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         Tile t[MT];
 #pragma unroll
@@ -601,7 +605,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       // non-consuming wait; its second completion needs MMAs that need more than two weight stages, so it cannot pass us).
       int ws = 0; uint32_t wphase = 0;
       int early = CG == 1 ? 2 : -1;
-      Tile walk = decode(sup_begin, 0);
+      Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         const Tile t = walk;
 #pragma unroll
@@ -653,7 +657,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       long long t_first_mma = 0;
       const bool dbg_on = p.dbg != nullptr;
       uint32_t b_cur = w_lo0, w_full_cur = w_full(0), w_empty_cur = w_empty(0);      // running per-stage values of ws
-      Tile walk = decode(sup_begin, 0);
+      Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
@@ -739,7 +743,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     int it = 0;
     HDBG_DECL();
-    Tile walk = decode(sup_begin, 0);
+    Tile walk = tile0;
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -833,7 +837,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 
     int it = 0, stg = 0;
     HDBG_DECL();
-    Tile walk = decode(sup_begin, 0);
+    Tile walk = tile0;
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -1019,7 +1023,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     int as = 0; uint32_t aphase = 0;
     bool first_halo_seen = false;
     HDBG_DECL();
-    Tile walk = decode(sup_begin, 0);
+    Tile walk = tile0;
     for (int sup = sup_begin; sup < sup_end; ++sup) {
       Tile t[MT];
 #pragma unroll
