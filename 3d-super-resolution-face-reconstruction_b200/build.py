@@ -30,12 +30,18 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, timing=False):
+    """timing=True builds libb200sr3_timing.so with the per-role cycle counters compiled in (-DB200SR3_ROLE_TIMING=1);
+    select it with B200SR3_LIB=<path> for tools/halo_bench.py runs under B200SR3_CONV_TIMING=1."""
+    global OUT, FLAGS
+    if timing:
+        OUT = OUT.replace("libb200sr3.so", "libb200sr3_timing.so")
+        FLAGS = FLAGS + ["-DB200SR3_ROLE_TIMING=1"]
     stamp = OUT + ".stamp"
     dig = _digest()
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_timing" if timing else "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
@@ -60,4 +66,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timing="--timing" in sys.argv))

@@ -244,10 +244,17 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Role timing is a COMPILE-TIME option (-DB200SR3_ROLE_TIMING=1, `build.py --timing` -> libb200sr3_timing.so): with the
+// counters compiled in, every hot loop carries parameter loads, clock reads and branches, and the kernel's hot code set
+// grows - measured, unrolling the nine taps of the issue loop alone (more code, fewer instructions executed) cost 6 %.
+#ifndef B200SR3_ROLE_TIMING
+#define B200SR3_ROLE_TIMING 0
+#endif
+#define HALO_DBG (B200SR3_ROLE_TIMING && p.dbg != nullptr)
 #define HDBG_DECL() unsigned long long hd[4] = {0ull, 0ull, 0ull, 0ull}; long long hd_t0 = 0
-#define HDBG_T0() do { if (p.dbg) hd_t0 = clock64(); } while (0)
-#define HDBG_ACC(i) do { if (p.dbg) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
-#define HDBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
+#define HDBG_T0() do { if (HALO_DBG) hd_t0 = clock64(); } while (0)
+#define HDBG_ACC(i) do { if (HALO_DBG) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
+#define HDBG_FLUSH(slot, n) do { if (HALO_DBG) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
 // (scale, shift) table of the fused GroupNorm for the IMGS images starting at image b0, built by the 256 transform threads
 // (tt = 0..255) into shared memory: gtab[im * gn_pitch + c + 2 * (c >> 3)] (10 float2 slots per 8 channels: the eight
@@ -412,7 +419,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     for (int i = 0; i < (int)(sizeof(ConvHaloParams) / 64); ++i) touch += pw[i * 16];
     asm volatile("" ::"r"(touch));
   }
-  const long long t_entry = p.dbg ? clock64() : 0;      // role timing: kernel entry on this SM (after the parameter touch)
+  const long long t_entry = HALO_DBG ? clock64() : 0;      // role timing: kernel entry on this SM (after the parameter touch)
 
   // contiguous run of super tiles; order: x tile fastest, y tile, parity, image, n tile. (32-bit arithmetic: the host
   // checks total_super * grid < 2^31; a 64-bit division is a ~500-cycle subroutine in front of the first TMA load.)
@@ -539,7 +546,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     tab_b_early = tile0.b;
     halo_build_gn_table<G::IMGS>(p, reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET), p.gn_C + 2 * (p.gn_C >> 3), tt,
                                  tab_b_early, p.gn_swish != 0);
-    if (p.dbg && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
+    if (HALO_DBG && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
   }
   if (GEO == 2) {
     // pixels 125 .. 134 of every stage: the zero row below the last image (TMA never writes them, nobody else does)
@@ -567,14 +574,14 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   if (p.pdl && warp != LW + 1) pdl_wait();
   uint32_t tmem_base = 0;
   if (CG == 2 || (warp != LW && warp != LW + 1)) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 15] = (unsigned long long)(clock64() - t_entry);   // [15] prologue
+  if (HALO_DBG && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 15] = (unsigned long long)(clock64() - t_entry);   // [15] prologue
 
   if (warp == LW) {
     if (ptx::elect_one()) {
       // ---------------------------------------------------------------- halo producer
       int as = 0; uint32_t aphase = 0;
       HDBG_DECL();
-      const long long hd_start = p.dbg ? clock64() : 0;
+      const long long hd_start = HALO_DBG ? clock64() : 0;
       Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup) {
         Tile t[MT];
@@ -593,7 +600,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           }
         }
       }
-      if (p.dbg) { hd[1] = (unsigned long long)(clock64() - hd_start); hd[2] = (unsigned long long)(sup_end - sup_begin); }
+      if (HALO_DBG) { hd[1] = (unsigned long long)(clock64() - hd_start); hd[2] = (unsigned long long)(sup_end - sup_begin); }
       HDBG_FLUSH(0, 3);      // [0] A producer waits a_empty, [1] total, [2] super tiles
     }
   } else if (warp == LW + 1) {
@@ -655,7 +662,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       int it = 0;
       HDBG_DECL();
       long long t_first_mma = 0;
-      const bool dbg_on = p.dbg != nullptr;
+      const bool dbg_on = HALO_DBG;
       uint32_t b_cur = w_lo0, w_full_cur = w_full(0), w_empty_cur = w_empty(0);      // running per-stage values of ws
       Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
@@ -722,7 +729,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       // be scheduled (they run their prologue and block in pdl_wait until this grid has completed)
       pdl_launch_dependents();
       HDBG_FLUSH(4, 3);      // [4] MMA waits A ready, [5] waits W full, [6] waits TMEM empty
-      if (p.dbg) {           // [12] kernel entry -> first MMA issued ("fill"), [13] entry -> last MMA issued
+      if (HALO_DBG) {           // [12] kernel entry -> first MMA issued ("fill"), [13] entry -> last MMA issued
         p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(t_first_mma - t_entry);
         p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)(clock64() - t_entry);
       }
@@ -1004,7 +1011,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     }
     if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
-    if (tid_e == 0 && p.dbg) p.dbg[blockIdx.x * 16 + 14] = (unsigned long long)(clock64() - t_entry);   // [14] entry -> epilogue done
+    if (tid_e == 0 && HALO_DBG) p.dbg[blockIdx.x * 16 + 14] = (unsigned long long)(clock64() - t_entry);   // [14] entry -> epilogue done
 #undef HALO_EPI_SYNC
   } else if (XF && (warp < 4 || (warp >= 8 && warp < 12))) {
     // ------------------------------------------------------------------ GroupNorm + Swish transform
@@ -1052,7 +1059,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           }
           ptx::mbar_wait(a_full(as), aphase);
           HDBG_ACC(0);
-          if (p.dbg && tt == 0 && !first_halo_seen) { first_halo_seen = true; p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry); }   // [7] first halo landed
+          if (HALO_DBG && tt == 0 && !first_halo_seen) { first_halo_seen = true; p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry); }   // [7] first halo landed
           HDBG_T0();
           if (seg.gn_off >= 0 && !(p.ablate & 2)) {
 #pragma unroll
