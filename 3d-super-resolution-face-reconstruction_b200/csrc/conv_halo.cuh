@@ -251,6 +251,7 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
 #define B200SR3_ROLE_TIMING 0
 #endif
 #define HALO_DBG (B200SR3_ROLE_TIMING && p.dbg != nullptr)
+#define HALO_ABLATE(bits) (B200SR3_ROLE_TIMING && (p.ablate & (bits)))      // measurement switches: same build option
 #define HDBG_DECL() unsigned long long hd[4] = {0ull, 0ull, 0ull, 0ull}; long long hd_t0 = 0
 #define HDBG_T0() do { if (HALO_DBG) hd_t0 = clock64(); } while (0)
 #define HDBG_ACC(i) do { if (HALO_DBG) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
@@ -474,10 +475,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   // kernel takes ~3 k cycles (caches and TLBs start cold at every launch) and used to begin after ~2 k cycles of setup.
   // One halo stage = the MT tiles' boxes of one 64-channel block, all completing on a_full(stage).
   auto issue_halo = [&](int stage, int map, int cb, const Tile* t) {
-    ptx::mbar_expect_tx(a_full(stage), (p.ablate & 8) ? 0 : MT * G::BYTES);
+    ptx::mbar_expect_tx(a_full(stage), HALO_ABLATE(8) ? 0 : MT * G::BYTES);
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      if (p.ablate & 8) break;
+      if HALO_ABLATE(8) break;
       if (GEO == 0)
         ptx::tma_load_4d(smem_base + stage * S::A_STAGE + m * G::STRIDE, &p.a_map[map], a_full(stage),
                          cb * CONV_BLOCK_K, t[m].x0 - 1, t[m].y0 - 1, t[m].b);
@@ -631,8 +632,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                 tma_load_2d_pair(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws) & HALO_PEER_MASK,
                                  seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
               } else {
-                ptx::mbar_expect_tx(w_full(ws), (p.ablate & 4) ? 0 : S::W_STAGE);
-                if (!(p.ablate & 4))
+                ptx::mbar_expect_tx(w_full(ws), HALO_ABLATE(4) ? 0 : S::W_STAGE);
+                if (!HALO_ABLATE(4))
                   ptx::tma_load_2d(smem_base + S::W_OFFSET + ws * S::W_STAGE, &p.w_map, w_full(ws),
                                    seg.k_base + tap * seg.k_tap_stride + cb * CONV_BLOCK_K, wrow);
               }
@@ -868,7 +869,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           if (lane == 0) bulk_wait_read<NSTG - 1>();
           __syncwarp();
           bf16* g2_dst = nullptr;             // GEO 2: this thread's output row in global memory (null: not an output)
-          if (GEO == 2 && ((g2_valid >> lane) & 1u) && !(p.ablate & 1)) {
+          if (GEO == 2 && ((g2_valid >> lane) & 1u) && !HALO_ABLATE(1)) {
             const int img = g2_first + (lane >= g2_rb ? 1 : 0);
             const int q = (32 * wq + lane) % 25, y = q / 5 - 1, x = q % 5 - 1;
             if (t.b + img < p.B) {
@@ -880,7 +881,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
-            if (!(p.ablate & 16)) {
+            if (!HALO_ABLATE(16)) {
               ptx::tmem_ld32(taddr + (uint32_t)(cc * 64 + half * 32), v);
               ptx::tmem_ld_wait();
             } else {
@@ -909,13 +910,13 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             __syncwarp();                   // rows were stored from registers; the slab only feeds the statistics
           } else {
             __syncwarp();
-            if (lane == 0 && !(p.ablate & 1)) {
+            if (lane == 0 && !HALO_ABLATE(1)) {
               if (GEO == 0) tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, t.x0, t.y0 + 4 * wq, t.b);
               else tma_store_4d(&p.o_map[t.par], sl, n0 + cc * 64, 0, t.b, 2 * wq);      // (C, W, B, H) view
               bulk_commit();
             }
           }
-          if (GEO == 2 && do_stats && !(p.ablate & 32)) {
+          if (GEO == 2 && do_stats && !HALO_ABLATE(32)) {
             // every element goes to fixed point on its own: which rows of an image a warp sees depends on the image's
             // place in the tile, and float partial sums would make a face's statistics depend on its batch position
 #pragma unroll
@@ -929,7 +930,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               else { acc[0][cc][0] += i0; acc[0][cc][1] += i1; acc[0][cc][2] += i2; acc[0][cc][3] += i3; }
             }
           }
-          if (GEO != 2 && do_stats && !(p.ablate & 32)) {
+          if (GEO != 2 && do_stats && !HALO_ABLATE(32)) {
             float s0[IMGS], s1[IMGS], q0[IMGS], q1[IMGS];
 #pragma unroll
             for (int im = 0; im < IMGS; ++im) s0[im] = s1[im] = q0[im] = q1[im] = 0.f;
@@ -1061,7 +1062,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           HDBG_ACC(0);
           if (HALO_DBG && tt == 0 && !first_halo_seen) { first_halo_seen = true; p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry); }   // [7] first halo landed
           HDBG_T0();
-          if (seg.gn_off >= 0 && !(p.ablate & 2)) {
+          if (seg.gn_off >= 0 && !HALO_ABLATE(2)) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
               // GEO 0: chunks 32 pixels apart cover the 180-pixel halo (the ring belongs to neighbouring

@@ -271,10 +271,15 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // role timing helpers (two accumulators per thread; only when p.dbg is set)
+#ifndef B200SR3_ROLE_TIMING
+#define B200SR3_ROLE_TIMING 0      // compile-time option (build.py --timing): counters and ablation switches cost hot-loop code
+#endif
+#define UMMA_DBG (B200SR3_ROLE_TIMING && p.dbg != nullptr)
+#define UMMA_ABLATE(bits) (B200SR3_ROLE_TIMING && (p.ablate & (bits)))
 #define DBG_DECL() unsigned long long dbg_acc[2] = {0ull, 0ull}; long long dbg_t0 = 0
-#define DBG_T0() do { if (p.dbg) dbg_t0 = clock64(); } while (0)
-#define DBG_ACC(i) do { if (p.dbg) dbg_acc[i] += (unsigned long long)(clock64() - dbg_t0); } while (0)
-#define DBG_FLUSH(slot, n) do { if (p.dbg) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 8 + (slot) + _i] = dbg_acc[_i]; } while (0)
+#define DBG_T0() do { if (UMMA_DBG) dbg_t0 = clock64(); } while (0)
+#define DBG_ACC(i) do { if (UMMA_DBG) dbg_acc[i] += (unsigned long long)(clock64() - dbg_t0); } while (0)
+#define DBG_FLUSH(slot, n) do { if (UMMA_DBG) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 8 + (slot) + _i] = dbg_acc[_i]; } while (0)
 
 // MMA_WARPS: a single warp can issue one tcgen05.mma per ~86 cycles (measured, tools/micro/
 // umma_rate*.cu), which only saturates the tensor pipe at N = 256 (128 cycles each). For N <= 128 two
@@ -373,11 +378,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               DBG_ACC(0);
               const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
               const uint32_t sb = sa + S::A_BYTES;
-              ptx::mbar_expect_tx(full_bar(stage), ((p.ablate & 2) ? 0 : S::A_BYTES) + ((p.ablate & 4) ? 0 : S::B_BYTES));
-              if (!(p.ablate & 2))
+              ptx::mbar_expect_tx(full_bar(stage), (UMMA_ABLATE(2) ? 0 : S::A_BYTES) + (UMMA_ABLATE(4) ? 0 : S::B_BYTES));
+              if (!UMMA_ABLATE(2))
                 ptx::tma_load_4d(sa, &p.a_map[tap.map], full_bar(stage), cb * CONV_BLOCK_K, t[j].w0 + tap.dw,
                                  t[j].h0 + tap.dh, t[j].b0);
-              if (!(p.ablate & 4))
+              if (!UMMA_ABLATE(4))
                 ptx::tma_load_2d(sb, &p.w_map, full_bar(stage), kb * CONV_BLOCK_K,
                                  t[j].par * p.Cout + t[j].n_tile * BLOCK_N);
               if (++rs[j] == RING) { rs[j] = 0; rphase[j] ^= 1u; }
@@ -467,7 +472,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 
     int it = 0;
     DBG_DECL();
-    const long long dbg_start = p.dbg ? clock64() : 0;
+    const long long dbg_start = UMMA_DBG ? clock64() : 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const Tile t = decode(tile);
       const int buf = it % NBUF;
@@ -488,7 +493,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
-        if (!(p.ablate & 16)) {
+        if (!UMMA_ABLATE(16)) {
           ptx::tmem_ld32(taddr + (uint32_t)c0, v);
           ptx::tmem_ld_wait();
         } else {
@@ -498,7 +503,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias && !(p.ablate & 8)) {
+        if (bias && !UMMA_ABLATE(8)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
@@ -506,7 +511,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
         }
         if (valid) {
-          if (res_row && !(p.ablate & 8)) {
+          if (res_row && !UMMA_ABLATE(8)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float r[8];
@@ -515,7 +520,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               for (int e = 0; e < 8; ++e) f[j + e] += r[e];
             }
           }
-          if (!(p.ablate & 1)) {
+          if (!UMMA_ABLATE(1)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(out_row + c0 + j) = pack8(f + j);
           }
@@ -567,7 +572,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
       }
     }
-    if (p.dbg && tid_e == 0) {
+    if (UMMA_DBG && tid_e == 0) {
       p.dbg[blockIdx.x * 8 + 4] = dbg_acc[0];                      // epilogue: waiting for an accumulator
       p.dbg[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - dbg_start);   // epilogue: total
       p.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(tile_end - tile_begin);
