@@ -357,7 +357,13 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       st.partial = (long long*)dalloc((size_t)B * st.slots * Cout * 2 * sizeof(long long));
     }
     const char* tev = getenv("B200SR3_CONV_TIMING");
-    const bool timing = tev && tev[0] == '1';
+    bool timing = tev && tev[0] == '1';
+#if !B200SR3_ROLE_TIMING
+    if (timing) {
+      fprintf(stderr, "b200sr3: this build has no role counters; build `build.py --timing` and set B200SR3_LIB to libb200sr3_timing.so\n");
+      timing = false;
+    }
+#endif
     if (timing) {
       st.dbg = (unsigned long long*)dalloc(256 * 16 * sizeof(unsigned long long));
       CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 16 * sizeof(unsigned long long)));

@@ -12,7 +12,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 
 echo "ncu list rc $?"
 for sh in "c1 512+256->256 @32:n256" "c1 128+64->64 @128:n64"; do
   name="${sh%%:*}"; tag="${sh##*:}"
-  B200SR3_CONV_TIMING=1 python tools/halo_bench.py 32 20 "$name" 1 > gpurun_out/${TAG}_roles_$tag.txt 2>&1
+  B200SR3_LIB=$PWD/3d-super-resolution-face-reconstruction_b200/b200sr3/libb200sr3_timing.so B200SR3_CONV_TIMING=1 \
+    python tools/halo_bench.py 32 20 "$name" 1 > gpurun_out/${TAG}_roles_$tag.txt 2>&1      # needs `build.py --timing`
   python tools/halo_bench.py 32 3 "$name" 1 > gpurun_out/${TAG}_plain_$tag.log 2>&1 && \
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 1 -c 1 -o gpurun_out/${TAG}_halo_$tag -f python tools/halo_bench.py 32 3 "$name" 1 > gpurun_out/${TAG}_ncu_$tag.log 2>&1
   echo "ncu full $tag rc $?"
