@@ -190,6 +190,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
   p.out = out.ptr;
   REQUIRE(!any_gn || gn_C <= 1024, "halo conv: the fused GroupNorm handles at most 1024 channels");
+  REQUIRE(!any_gn || gn_swish, "halo conv: the fused GroupNorm is always followed by Swish (unet.py:84-86)");
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
   if (any_gn && gn_from_stats) {
     const GnPlan& g = *gn_from_stats;

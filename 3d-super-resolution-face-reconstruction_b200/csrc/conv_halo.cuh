@@ -1024,7 +1024,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;      // 0..255
     const int j = tt & 7;
     const int p_first = tt >> 3;
-    const bool do_swish = p.gn_swish != 0;
+    constexpr bool do_swish = true;      // Block = GroupNorm -> Swish -> Conv (unet.py:84-86): the host rejects a fused GroupNorm without Swish
     float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C (padded)], halved if swish
     const int gn_pitch = p.gn_C + 2 * (p.gn_C >> 3);
     int tab_b = tab_b_early;
