@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SR3_LIB selects another build of the same library (same-box A/B runs of two kernel variants)
 LIB_PATH = os.environ.get("B200SR3_LIB") or os.path.join(_HERE, "libb200sr3.so")
 MAX_LEVELS = 8
+ABI_VERSION = 2          # B200SR3_ABI_VERSION of include/b200sr3.h
 NOISE_INJECTED = 1
 NOISE_PHILOX = 2
 
@@ -36,10 +37,11 @@ _SIGNATURES = {
     "b200sr3_finalize_weights": (C.c_int, [_P, _P]),
     "b200sr3_set_schedule": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "b200sr3_unet_forward": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, C.c_int, _P, _P]),
-    "b200sr3_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
-    "b200sr3_sample": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint64, C.c_int, C.c_int, _P, _P, _P]),
+    "b200sr3_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "b200sr3_sample": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint64, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
+    "b200sr3_philox_normal": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "b200sr3_num_snapshots": (C.c_int, [_P]),
-    "b200sr3_sample_host": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
+    "b200sr3_sample_host": (C.c_int, [_P, _P, C.c_uint64, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "b200sr3_layer_output": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "b200sr3_last_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200sr3_profile_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
@@ -73,7 +75,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.b200sr3_abi_version() != 1:
+    if lib.b200sr3_abi_version() != ABI_VERSION:
         raise ImportError("libb200sr3.so ABI version mismatch")
     _lib = lib
     return lib

@@ -47,9 +47,19 @@ def load_network(netG, load_path, strict=True):
     return _load(netG, torch.load(gen_path, map_location="cpu", weights_only=True), strict)
 
 
-def load_combined(netG, path, strict=False):
-    """lib/trainer_temp.py:165-188: the SR generator out of a combined checkpoint (`sr_model_state`)."""
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+def load_combined(netG, path, strict=False, allow_pickle=False):
+    """lib/trainer_temp.py:165-188: the SR generator out of a combined checkpoint (`sr_model_state`).
+
+    Loaded with torch's restricted unpickler (tensors and plain containers only). A combined checkpoint that also
+    pickles arbitrary Python objects (the reference stores optimizer state and the config node beside the weights) is
+    refused unless the caller opts in with allow_pickle=True - unpickling executes code from the file."""
+    try:
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:          # pickle.UnpicklingError from the allow-list
+        if not allow_pickle:
+            raise RuntimeError(f"b200sr3: '{path}' holds objects torch's safe loader refuses ({e}); pass "
+                               "allow_pickle=True only for a checkpoint you trust") from e
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
     if "sr_model_state" not in ckpt:
         raise KeyError("b200sr3: not a combined checkpoint (no 'sr_model_state')")
     return _load(netG, ckpt["sr_model_state"], strict)

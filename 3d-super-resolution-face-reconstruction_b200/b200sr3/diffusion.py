@@ -81,8 +81,8 @@ class GaussianDiffusion(nn.Module):
         self._engines = {}
         self._sched_host = None
         self._sched_serial = 0
-        self.noise_seed = 0       # base seed of the in-kernel Philox stream
-        self._calls = 0
+        self.noise_seed = None    # fixed seed of the in-kernel Philox stream; None: drawn from torch's global generator
+        self._weights_serial = 0  # bumped by invalidate_weights(): the engines repack before their next call
 
     def __getstate__(self):       # engines hold device handles: never pickled / deep-copied
         state = self.__dict__.copy()
@@ -135,6 +135,29 @@ class GaussianDiffusion(nn.Module):
         self._sched_serial += 1
 
     # ------------------------------------------------------------------ engine plumbing
+    def invalidate_weights(self):
+        """Tell the engines that parameter VALUES changed, so the bf16 operands are repacked before the next sampling
+        call. In-place edits through autograd-visible ops (`p.copy_`, `p.zero_` under no_grad, optimizer steps) and
+        storage changes (`.to()`, `.cuda()`, `load_state_dict`) are detected automatically; edits through `p.data`
+        (the reference's finetune_norm `v.data.zero_()`, model/sr/model.py:45, and EMA-style `p.data.copy_()`) bump a
+        separate version counter torch does not expose on the parameter - call this after them."""
+        self._weights_serial += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weights()
+        return out
+
+    def _next_seed(self, seed):
+        """Seed of the Philox stream for one sampling call. Like the reference, whose noise comes from torch's global
+        generator (diffusion.py:186,205), the default is drawn from that generator: torch.manual_seed() makes runs
+        reproducible, and ranks seeded alike agree on the stream (rows are told apart by `row_offset`)."""
+        if seed is not None:
+            return int(seed) & (2 ** 64 - 1)
+        if self.noise_seed is not None:
+            return int(self.noise_seed) & (2 ** 64 - 1)
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
     def _sampling_device(self):
         dev = self.betas.device if hasattr(self, "betas") else next(self.denoise_fn.parameters()).device
         if dev.type != "cuda":
@@ -152,16 +175,25 @@ class GaussianDiffusion(nn.Module):
         if eng is None:
             eng = self._engines[idx] = _Engine(self._cfg, idx)
         params = self.denoise_fn.tensors()
-        version = tuple((p.data_ptr(), p._version) for _, p in params)
+        # staleness: storage identity and torch's version counters folded into two integers (plus the explicit serial)
+        ptrs = vers = 0
+        for _, p in params:
+            ptrs ^= p.data_ptr()
+            vers += p._version
+        version = (self._weights_serial, ptrs, vers)
         if eng.weights_version != version:
             with torch.cuda.device(idx):
+                staged = []
                 for key, p in params:
                     t = p.detach()
                     if t.device.type != "cuda" or t.device.index != idx or t.dtype != torch.float32 or not t.is_contiguous():
                         t = t.to(device=f"cuda:{idx}", dtype=torch.float32).contiguous()
+                    staged.append((key, t))
+                torch.cuda.current_stream().synchronize()      # once: the library copies on its own stream
+                for key, t in staged:
                     shape = (C.c_int64 * t.dim())(*t.shape)
-                    torch.cuda.current_stream().synchronize()
                     _lib.check(eng.lib.b200sr3_load_tensor(eng.handle, key.encode(), _ptr(t), shape, t.dim()))
+                del staged
                 _lib.check(eng.lib.b200sr3_finalize_weights(eng.handle, _stream()))
             eng.weights_version = version
         if getattr(self, "num_timesteps", None) and eng.schedule_version != self._sched_serial:
@@ -195,8 +227,6 @@ class GaussianDiffusion(nn.Module):
     def p_sample(self, x, t, clip_denoised=True, condition_x=None, noise=None):
         """diffusion.py:182-187. `noise` injects z_t; when None it is drawn with torch.randn_like
         exactly where the reference draws it, so the global RNG stream is consumed identically."""
-        if not clip_denoised:
-            raise NotImplementedError("b200sr3: the fused update always clips x0 (the reference default)")
         dev = self._sampling_device()
         eng = self._engine(dev)
         x = self._as_input(x, dev)
@@ -206,18 +236,20 @@ class GaussianDiffusion(nn.Module):
         z = self._as_input(noise, dev) if (noise is not None and t > 0) else None
         out = torch.empty_like(x)
         with torch.cuda.device(dev):
-            _lib.check(eng.lib.b200sr3_step(eng.handle, _ptr(cond), _ptr(x), _ptr(z), int(t), x.shape[0], x.shape[-1],
-                                            _ptr(out), _stream()))
+            _lib.check(eng.lib.b200sr3_step(eng.handle, _ptr(cond), _ptr(x), _ptr(z), int(t), 1 if clip_denoised else 0,
+                                            x.shape[0], x.shape[-1], _ptr(out), _stream()))
         return out
 
     @torch.no_grad()
-    def sample_batched(self, x_in, noise=None, seed=None, return_snapshots=False):
+    def sample_batched(self, x_in, noise=None, seed=None, return_snapshots=False, row_offset=0, return_x_T=False):
         """All T steps for a whole batch: the entry point benchmarks and parity tests use.
 
         x_in: cond [B,3,R,R] (conditional) — or a shape tuple for unconditional models.
         noise: optional injected list [T,B,3,R,R] = [x_T, z_{T-1}, ..., z_1]; otherwise the
-        in-kernel Philox stream with `seed` (default: noise_seed + call counter).
-        Returns x_0 [B,3,R,R] (and the `continous=True` snapshots [n,B,3,R,R] if asked).
+        in-kernel Philox stream with `seed` (default: `noise_seed`, else drawn from torch's global generator).
+        row_offset: global index of batch row 0 in the Philox stream - shards / chunks of one logical batch pass
+        their start row and the same seed, and every face gets the noise it would get in the unsplit batch.
+        Returns x_0 [B,3,R,R] (then the `continous=True` snapshots [n,B,3,R,R] and / or x_T if asked).
         """
         dev = self._sampling_device()
         eng = self._engine(dev)
@@ -239,23 +271,45 @@ class GaussianDiffusion(nn.Module):
                 raise ValueError(f"b200sr3: injected noise must have shape {(self.num_timesteps,) + shape}")
             mode, sd = _lib.NOISE_INJECTED, 0
         else:
-            mode = _lib.NOISE_PHILOX
-            sd = (self.noise_seed + self._calls) if seed is None else int(seed)
-            self._calls += 1
+            mode, sd = _lib.NOISE_PHILOX, self._next_seed(seed)
         with torch.cuda.device(dev):
-            _lib.check(eng.lib.b200sr3_sample(eng.handle, _ptr(cond), mode, _ptr(noise), C.c_uint64(sd & (2 ** 64 - 1)),
-                                              B, R, _ptr(out), _ptr(snaps), _stream()))
-        return (out, snaps) if return_snapshots else out
+            _lib.check(eng.lib.b200sr3_sample(eng.handle, _ptr(cond), mode, _ptr(noise), C.c_uint64(sd),
+                                              C.c_int64(int(row_offset)), B, R, _ptr(out), _ptr(snaps), _stream()))
+        res = (out,) + ((snaps,) if return_snapshots else ())
+        if return_x_T:
+            if noise is not None:
+                x_T = noise[0].clone()
+            else:
+                x_T = torch.empty(shape, dtype=torch.float32, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(eng.lib.b200sr3_philox_normal(eng.handle, C.c_uint64(sd), int(self.num_timesteps),
+                                                             C.c_int64(int(row_offset)), B, R, _ptr(x_T), _stream()))
+            res = res + (x_T,)
+        return res if len(res) > 1 else out
+
+    @torch.no_grad()
+    def philox_normal(self, shape, t, seed, row_offset=0):
+        """The sampler's own N(0,1) stream: the draw the Philox mode makes at key t (t = num_timesteps: x_T,
+        diffusion.py:205; 0 < t < T: z_t, diffusion.py:186) for rows row_offset.. of the global batch."""
+        dev = self._sampling_device()
+        eng = self._engine(dev)
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(eng.lib.b200sr3_philox_normal(eng.handle, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(t),
+                                                     C.c_int64(int(row_offset)), out.shape[0], out.shape[-1], _ptr(out),
+                                                     _stream()))
+        return out
 
     @torch.no_grad()
     def p_sample_loop(self, x_in, continous=False, noise=None, seed=None):
         """diffusion.py:189-215, including its return convention: `continous=True` returns
         cat([x_in, snapshots...], 0); otherwise ONLY the last batch element, shape [3,R,R]."""
         if continous:
-            out, snaps = self.sample_batched(x_in, noise=noise, seed=seed, return_snapshots=True)
-            head = self._as_input(x_in, out.device) if self.conditional else None
+            # the list starts with x_in (conditional, diffusion.py:203-204) or with x_T (unconditional, :195-196)
+            out, snaps, x_T = self.sample_batched(x_in, noise=noise, seed=seed, return_snapshots=True, return_x_T=True)
+            head = self._as_input(x_in, out.device) if self.conditional else x_T
             flat = snaps.reshape((-1,) + tuple(snaps.shape[2:]))
-            return torch.cat([head, flat], dim=0) if head is not None else flat
+            return torch.cat([head, flat], dim=0)
         return self.sample_batched(x_in, noise=noise, seed=seed)[-1]
 
     @torch.no_grad()
@@ -267,9 +321,9 @@ class GaussianDiffusion(nn.Module):
         return self.p_sample_loop(x_in, continous, noise=noise, seed=seed)
 
     @torch.no_grad()
-    def super_resolution_batched(self, x_in, noise=None, seed=None):
+    def super_resolution_batched(self, x_in, noise=None, seed=None, row_offset=0):
         """[B,3,R,R] in -> [B,3,R,R] out (the reference returns only the last element)."""
-        return self.sample_batched(x_in, noise=noise, seed=seed)
+        return self.sample_batched(x_in, noise=noise, seed=seed, row_offset=row_offset)
 
     @torch.no_grad()
     def super_resolution_samples(self, x_in, n_samples, noise=None, seed=None, max_batch=None):
@@ -279,8 +333,10 @@ class GaussianDiffusion(nn.Module):
         LR input one after the other at B=1 (lib/trainer_temp.py:441-444 calling model/sr3d/model.py:366 test_val,
         each a full super_resolution call). Chains are independent, so they stack along the batch: image i, sample k
         sits at row i*n_samples + k. x_in [B,3,R,R] -> [B, n_samples, 3, R, R]. `noise` (optional, parity runs):
-        [T, B*n_samples, 3, R, R] in that row order; otherwise Philox with `seed`. `max_batch` bounds the rows per
-        launch chain (the workspace is sized per batch); every row's result is independent of the chunking."""
+        [T, B*n_samples, 3, R, R] in that row order; otherwise Philox with ONE `seed` for the whole call, keyed by the
+        global row i*n_samples + k. `max_batch` bounds the rows per launch chain (the workspace is sized per batch);
+        in both noise modes every row's result is independent of the chunking (chunks pass their start row as the
+        stream's row offset)."""
         n = int(n_samples)
         if n < 1:
             raise ValueError("b200sr3: n_samples must be >= 1")
@@ -292,16 +348,16 @@ class GaussianDiffusion(nn.Module):
         if noise is not None and step < total:
             noise = self._as_input(noise, dev)
         outs = []
-        for i, lo in enumerate(range(0, total, step)):
+        sd = None if noise is not None else self._next_seed(seed)
+        for lo in range(0, total, step):
             hi = min(total, lo + step)
             nz = None if noise is None else noise[:, lo:hi].contiguous()
-            sd = None if seed is None else int(seed) + i
-            outs.append(self.sample_batched(rows[lo:hi].contiguous(), noise=nz, seed=sd))
+            outs.append(self.sample_batched(rows[lo:hi].contiguous(), noise=nz, seed=sd, row_offset=lo))
         out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         return out.reshape((cond.shape[0], n) + tuple(out.shape[1:]))
 
     @torch.no_grad()
-    def sample_host(self, cond_host, out_host=None, seed=0):
+    def sample_host(self, cond_host, out_host=None, seed=0, row_offset=0):
         """End-to-end call on HOST tensors (pinned for full PCIe speed): cond is copied to the
         device, the full chain runs with Philox noise, the result is copied back; returns when
         the copy has landed. This is the path bench.py reports as `e2e`."""
@@ -313,8 +369,8 @@ class GaussianDiffusion(nn.Module):
             out_host = torch.empty_like(cond_host, pin_memory=True)
         B, R = cond_host.shape[0], cond_host.shape[-1]
         with torch.cuda.device(dev):
-            _lib.check(eng.lib.b200sr3_sample_host(eng.handle, _ptr(cond_host), C.c_uint64(int(seed)), B, R,
-                                                   _ptr(out_host), _stream()))
+            _lib.check(eng.lib.b200sr3_sample_host(eng.handle, _ptr(cond_host), C.c_uint64(self._next_seed(seed)),
+                                                   C.c_int64(int(row_offset)), B, R, _ptr(out_host), _stream()))
         return out_host
 
     def profile_step(self, B, R):

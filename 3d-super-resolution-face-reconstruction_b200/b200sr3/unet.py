@@ -125,12 +125,15 @@ class UNet(nn.Module):
         node.register_parameter("bias", nn.Parameter(torch.zeros(channels)))
 
     def init_orthogonal(self):
-        """What define_G applies when opt['phase'] == 'train' (networks.py:44-57, 110-112)."""
-        for name, p in self.named_parameters():
-            if name.endswith(".weight") and p.dim() >= 2:
-                nn.init.orthogonal_(p.data, gain=1)
-            elif name.endswith(".bias") and ("block.0" not in name and "norm" not in name):
-                p.data.zero_()
+        """What define_G applies when opt['phase'] == 'train' (networks.py:44-57, 110-112). Writes through the
+        parameters themselves (not `.data`), so their version counters move and a sampling engine that already packed
+        the old values repacks (GaussianDiffusion._engine)."""
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.endswith(".weight") and p.dim() >= 2:
+                    nn.init.orthogonal_(p, gain=1)
+                elif name.endswith(".bias") and ("block.0" not in name and "norm" not in name):
+                    p.zero_()
 
     def tensors(self):
         """(key, tensor) pairs in the naming libb200sr3 expects (no 'denoise_fn.' prefix)."""

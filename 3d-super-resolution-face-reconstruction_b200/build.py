@@ -21,48 +21,51 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-cudart", "static"]
 
 
-def _digest():
+def _digest(flags):
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(flags).encode())
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, timing=False):
+def build(force=False, verbose=False, timing=False, extra_flags=(), out=None):
     """timing=True builds libb200sr3_timing.so with the per-role cycle counters compiled in (-DB200SR3_ROLE_TIMING=1);
-    select it with B200SR3_LIB=<path> for tools/halo_bench.py runs under B200SR3_CONV_TIMING=1."""
-    global OUT, FLAGS
+    select it with B200SR3_LIB=<path> for tools/halo_bench.py runs under B200SR3_CONV_TIMING=1. `extra_flags` / `out`
+    build a variant library beside the default one (same-box A/B runs through B200SR3_LIB)."""
+    flags = list(FLAGS) + list(extra_flags)
+    target = out or OUT
     if timing:
-        OUT = OUT.replace("libb200sr3.so", "libb200sr3_timing.so")
-        FLAGS = FLAGS + ["-DB200SR3_ROLE_TIMING=1"]
-    stamp = OUT + ".stamp"
-    dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return OUT
-    objdir = os.path.join(HERE, "build_timing" if timing else "build")
+        target = target.replace("libb200sr3.so", "libb200sr3_timing.so")
+        flags.append("-DB200SR3_ROLE_TIMING=1")
+    stamp = target + ".stamp"
+    dig = _digest(flags)
+    if not force and os.path.exists(target) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return target
+    tag = os.path.basename(target).replace("libb200sr3", "").replace(".so", "")
+    objdir = os.path.join(HERE, "build" + tag)
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        out_text, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- nvcc {src}\n{out}\n")
+            sys.stderr.write(f"--- nvcc {src}\n{out_text}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [NVCC, "-shared", "-cudart", "static", "-o", OUT] + objs + ["-Xlinker", "--exclude-libs,ALL"]
+    link = [NVCC, "-shared", "-cudart", "static", "-o", target] + objs + ["-Xlinker", "--exclude-libs,ALL"]
     subprocess.run(link, check=True)
     with open(stamp, "w") as f:
         f.write(dig)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":

@@ -96,14 +96,21 @@ int b200sr3_unet_forward(b200sr3_handle* h, const float* cond, const float* x, f
   return guarded([&] { E(h).unet_forward(cond, x, noise_level, B, R, eps, (cudaStream_t)stream); });
 }
 
-int b200sr3_step(b200sr3_handle* h, const float* cond, const float* x_t, const float* noise, int t, int B, int R,
-                 float* x_tm1, void* stream) {
-  return guarded([&] { E(h).step(cond, x_t, noise, t, B, R, x_tm1, (cudaStream_t)stream); });
+int b200sr3_step(b200sr3_handle* h, const float* cond, const float* x_t, const float* noise, int t, int clip_denoised,
+                 int B, int R, float* x_tm1, void* stream) {
+  return guarded([&] { E(h).step(cond, x_t, noise, t, clip_denoised, B, R, x_tm1, (cudaStream_t)stream); });
 }
 
-int b200sr3_sample(b200sr3_handle* h, const float* cond, int noise_mode, const float* noise, uint64_t seed, int B,
-                   int R, float* out, float* snapshots, void* stream) {
-  return guarded([&] { E(h).sample(cond, noise_mode, noise, seed, B, R, out, snapshots, (cudaStream_t)stream); });
+int b200sr3_sample(b200sr3_handle* h, const float* cond, int noise_mode, const float* noise, uint64_t seed,
+                   int64_t row_offset, int B, int R, float* out, float* snapshots, void* stream) {
+  return guarded([&] {
+    E(h).sample(cond, noise_mode, noise, seed, row_offset, B, R, out, snapshots, (cudaStream_t)stream);
+  });
+}
+
+int b200sr3_philox_normal(b200sr3_handle* h, uint64_t seed, int t, int64_t row_offset, int B, int R, float* out,
+                          void* stream) {
+  return guarded([&] { E(h).philox_normal(seed, t, row_offset, B, R, out, (cudaStream_t)stream); });
 }
 
 int b200sr3_num_snapshots(b200sr3_handle* h) {
@@ -112,9 +119,9 @@ int b200sr3_num_snapshots(b200sr3_handle* h) {
   return n;
 }
 
-int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int B, int R, float* out_host,
-                        void* stream) {
-  return guarded([&] { E(h).sample_host(cond_host, seed, B, R, out_host, (cudaStream_t)stream); });
+int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int64_t row_offset, int B, int R,
+                        float* out_host, void* stream) {
+  return guarded([&] { E(h).sample_host(cond_host, seed, row_offset, B, R, out_host, (cudaStream_t)stream); });
 }
 
 int b200sr3_layer_output(b200sr3_handle* h, const char* layer, float* dst, int* C, int* H, int* W, void* stream) {

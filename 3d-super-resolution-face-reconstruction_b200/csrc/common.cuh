@@ -41,10 +41,12 @@ struct StepCtl {
   int t;               // current timestep (row of the schedule / noise-bias tables)
   int T;               // schedule length; row T of the bias table is the scratch row
   int noise_mode;      // 0: zeros, 1: injected list, 2: philox, 3: direct pointer (one step)
-  int pad;
+  int no_clip;         // 1: p_mean_variance(clip_denoised=False), x0 is not clamped (diffusion.py:175-176); 0 = the default
   const float* noise;  // list base (mode 1) or this step's z (mode 3)
   unsigned long long seed;
   long long numel;     // B*3*R*R, stride between entries of the injected list
+  long long row0;      // global index of this call's batch row 0: the Philox stream is keyed by GLOBAL (row, y, x), so a
+                       // face's noise does not depend on how a batch is sharded over ranks or chunked over calls
 };
 
 // ------------------------------------------------------------------------------- launches
@@ -131,10 +133,11 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(r * cs, r * sn);
 }
 // The reference's update, op for op (diffusion.py:150-151, 175-176, 159-160, 186-187).
+// `lim` = 1 (clip_denoised=True, the only value the reference's sampler uses) or +inf (clip_denoised=False).
 __device__ __forceinline__ float posterior_update(float x, float eps, float z, float a, float bc,
-                                                  float c1, float c2, float sigma) {
+                                                  float c1, float c2, float sigma, float lim = 1.0f) {
   float x0 = __fsub_rn(__fmul_rn(a, x), __fmul_rn(bc, eps));
-  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  x0 = fminf(fmaxf(x0, -lim), lim);
   const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
   return __fadd_rn(mean, __fmul_rn(z, sigma));
 }

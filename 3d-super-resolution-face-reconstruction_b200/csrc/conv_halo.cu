@@ -308,9 +308,15 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   op.is_conv = true;
   {
     const double m = (double)out.B * out.H * out.W;
-    double k = 0;
-    for (const HaloSource& s : srcs) k += (double)s.ntaps * s.act.C;    // reference graph: full 3x3 at output res
+    double k = 0, k_exec = 0;
+    for (const HaloSource& s : srcs) {
+      // reference graph: full 3x3 at output resolution; a res_conv segment counts, an identity shortcut
+      // that merely rides the GEMM (unet.py:101, nn.Identity) does not
+      if (!(s.ntaps == 1 && w.res_identity)) k += (double)s.ntaps * s.act.C;
+      k_exec += (double)(s.ntaps == 1 ? 1 : main_taps) * s.act.C;
+    }
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
+    op.flops_executed = 2.0 * m * (double)out.C * k_exec;
   }
   op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2](cudaStream_t s) {
     if (cg == 2) {

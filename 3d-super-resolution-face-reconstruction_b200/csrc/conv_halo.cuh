@@ -742,10 +742,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int lx = row & 7, ly = row >> 3;
     const int OC = p.tail_oc;
     const size_t plane = (size_t)p.H * p.W;
-    float a = 0.f, bc = 0.f, c1 = 0.f, c2 = 0.f, sigma = 0.f;
+    float a = 0.f, bc = 0.f, c1 = 0.f, c2 = 0.f, sigma = 0.f, lim = 1.0f;
     int ts = 0, T = 0, mode = 0;
     if (p.tail_x) {
       ts = p.ctl->t; T = p.ctl->T; mode = p.ctl->noise_mode;
+      if (p.ctl->no_clip) lim = __int_as_float(0x7f800000);      // clip_denoised=False: clamp to +-inf
       a = p.coefs[ts]; bc = p.coefs[T + ts]; c1 = p.coefs[2 * T + ts]; c2 = p.coefs[3 * T + ts];
       sigma = expf(0.5f * p.coefs[4 * T + ts]);
     }
@@ -768,7 +769,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         ptx::tmem_ld_wait();
         const int y = t.y0 + ly, x = t.x0 + lx;
         const size_t base = (size_t)t.b * OC * plane + (size_t)y * p.W + x;
-        const long long pix = ((long long)t.b * p.H + y) * p.W + x;
+        const long long pix = ((p.ctl->row0 + (long long)t.b) * p.H + y) * p.W + x;      // global row: sharding-invariant noise
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.tail_x && ts > 0) {
           if (mode == 1 || mode == 3) {
@@ -793,7 +794,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             if (p.tail_eps) p.tail_eps[base + o * plane] = eps;
             if (p.tail_x) {
               const float xv = p.tail_x[base + o * plane];
-              p.tail_x[base + o * plane] = posterior_update(xv, eps, z[o], a, bc, c1, c2, sigma);
+              p.tail_x[base + o * plane] = posterior_update(xv, eps, z[o], a, bc, c1, c2, sigma, lim);
             }
           }
         }

@@ -246,8 +246,11 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
   op.is_conv = true;
   {
     const double m = (double)out.B * out.H * out.W;
-    const double k = (double)main.taps * a.C + (res0 ? res0->C : 0) + (res1 ? res1->C : 0);
-    op.flops = 2.0 * m * (double)out.C * k;     // reference graph (full-resolution 3x3 for Upsample)
+    const double kres = (double)((res0 ? res0->C : 0) + (res1 ? res1->C : 0));
+    // reference graph: full-resolution 3x3 for Upsample; a res_conv counts, an identity shortcut that
+    // merely rides the GEMM (unet.py:101, nn.Identity) does not
+    op.flops = 2.0 * m * (double)out.C * ((double)main.taps * a.C + (w.res_identity ? 0.0 : kres));
+    op.flops_executed = 2.0 * m * (double)out.C * ((double)(up ? 4 : main.taps) * a.C + kres);
   }
   op.run = [pp, grid, bn](cudaStream_t s) {
     if (bn == 256) launch_conv<256, ST256, 1>(*pp, grid, s);

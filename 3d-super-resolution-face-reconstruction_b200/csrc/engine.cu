@@ -81,28 +81,41 @@ Engine::Engine(const b200sr3_config& cfg, int device) : cfg_(cfg), device_(devic
     throw Error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                 std::to_string(prop.minor) + "; b200sr3 is built for sm_100a (B200) only");
   CUDA_CHECK(cudaSetDevice(device));
-  conv_init_device();
-  CUDA_CHECK(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaMalloc(&ctl_, sizeof(StepCtl)));
-  CUDA_CHECK(cudaMemset(ctl_, 0, sizeof(StepCtl)));
-  if (const char* g = getenv("B200SR3_NO_GRAPH")) use_graph_ = !(g[0] == '1');
-  if (const char* g = getenv("B200SR3_BLOCK_N")) force_block_n_ = atoi(g);
-  if (const char* g = getenv("B200SR3_NO_FUSED_STATS")) fuse_stats_ = !(g[0] == '1');
-  if (const char* g = getenv("B200SR3_NO_HALO")) use_halo_ = !(g[0] == '1');
-  build_layers();
+  try {
+    conv_init_device();
+    CUDA_CHECK(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaMalloc(&ctl_, sizeof(StepCtl)));
+    CUDA_CHECK(cudaMemset(ctl_, 0, sizeof(StepCtl)));
+    if (const char* g = getenv("B200SR3_NO_GRAPH")) use_graph_ = !(g[0] == '1');
+    if (const char* g = getenv("B200SR3_BLOCK_N")) force_block_n_ = atoi(g);
+    if (const char* g = getenv("B200SR3_NO_FUSED_STATS")) fuse_stats_ = !(g[0] == '1');
+    if (const char* g = getenv("B200SR3_NO_HALO")) use_halo_ = !(g[0] == '1');
+    if (const char* g = getenv("B200SR3_MAX_WORKSPACES")) max_workspaces_ = (size_t)std::max(1, atoi(g));
+    build_layers();
+  } catch (...) {
+    release();          // a throwing constructor runs no destructor
+    throw;
+  }
 }
 
-Engine::~Engine() {
+void Engine::release() {
   cudaSetDevice(device_);
   workspaces_.clear();
   for (auto& t : tensors_) if (t.dev) cudaFree(t.dev);
+  tensors_.clear();
   for (void* p : owned_) cudaFree(p);
+  owned_.clear();
   if (coefs_) cudaFree(coefs_);
   if (nl_) cudaFree(nl_);
   if (table_) cudaFree(table_);
   if (ctl_) cudaFree(ctl_);
   if (capture_stream_) cudaStreamDestroy(capture_stream_);
+  coefs_ = nl_ = table_ = nullptr;
+  ctl_ = nullptr;
+  capture_stream_ = nullptr;
 }
+
+Engine::~Engine() { release(); }
 
 void Engine::add_tensor(const std::string& key, std::vector<int64_t> shape) {
   TensorSpec t;
@@ -253,6 +266,7 @@ void Engine::finalize_weights(cudaStream_t s) {
                   const std::string& reskey, int c_res0, int c_res1) {
     PackedConv pc;
     pc.cout = cout; pc.taps = taps; pc.cin_main = cin; pc.c_res0 = c_res0; pc.c_res1 = c_res1;
+    pc.res_identity = c_res0 && reskey == "identity";
     const int cpad = round_up(cin, CONV_BLOCK_K);
     const int r0pad = c_res0 ? round_up(c_res0, CONV_BLOCK_K) : 0;
     const int r1pad = c_res1 ? round_up(c_res1, CONV_BLOCK_K) : 0;
@@ -402,16 +416,29 @@ Workspace& Engine::workspace(int B, int R) {
     CUDA_CHECK(cudaMalloc(&nl_, sizeof(float)));
     CUDA_CHECK(cudaMalloc(&table_, (size_t)noise_total_ * sizeof(float)));
   }
-  auto key = std::make_pair(B, R);
-  auto it = workspaces_.find(key);
-  if (it != workspaces_.end()) return *it->second;
-  std::unique_ptr<Workspace> ws(new Workspace());
-  ws->B = B;
-  ws->R = R;
-  build_workspace(*ws);
-  Workspace& ref = *ws;
-  workspaces_[key] = std::move(ws);
-  return ref;
+  for (size_t i = 0; i < workspaces_.size(); ++i)
+    if (workspaces_[i]->B == B && workspaces_[i]->R == R) {      // hit: move to the most-recently-used end
+      std::rotate(workspaces_.begin() + i, workspaces_.begin() + i + 1, workspaces_.end());
+      return *workspaces_.back();
+    }
+  while (workspaces_.size() >= max_workspaces_) workspaces_.erase(workspaces_.begin());      // evict the LRU plan
+  for (;;) {
+    std::unique_ptr<Workspace> ws(new Workspace());
+    ws->B = B;
+    ws->R = R;
+    try {
+      build_workspace(*ws);
+    } catch (const Error&) {
+      // out of device memory: drop the other cached plans (oldest first) and retry before giving up
+      ws.reset();
+      cudaGetLastError();
+      if (workspaces_.empty()) throw;
+      workspaces_.erase(workspaces_.begin());
+      continue;
+    }
+    workspaces_.push_back(std::move(ws));
+    return *workspaces_.back();
+  }
 }
 
 void Engine::build_workspace(Workspace& ws) {
@@ -666,10 +693,11 @@ void Engine::build_workspace(Workspace& ws) {
   }
 }
 
-void Engine::write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, cudaStream_t s) {
+void Engine::write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, long long row0,
+                       cudaStream_t s, bool clip) {
   StepCtl c;
-  c.t = t; c.T = T_sched_; c.noise_mode = mode; c.pad = 0;
-  c.noise = noise; c.seed = seed; c.numel = numel;
+  c.t = t; c.T = T_sched_; c.noise_mode = mode; c.no_clip = clip ? 0 : 1;
+  c.noise = noise; c.seed = seed; c.numel = numel; c.row0 = row0;
   CUDA_CHECK(cudaMemcpyAsync(ctl_, &c, sizeof(c), cudaMemcpyHostToDevice, s));
 }
 
@@ -707,8 +735,8 @@ int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, do
   const int n = (int)ws.ops.size();
   REQUIRE(n <= max_ops, "profile_step: output arrays too small");
   const size_t numel = (size_t)B * cfg_.out_channel * R * R;
-  launch_philox_fill(ws.x, B, cfg_.out_channel, R, 1234, T_sched_, s);
-  write_ctl(T_sched_ - 1, B200SR3_NOISE_PHILOX, nullptr, 1234, (long long)numel, s);
+  launch_philox_fill(ws.x, B, cfg_.out_channel, R, 1234, T_sched_, 0, s);
+  write_ctl(T_sched_ - 1, B200SR3_NOISE_PHILOX, nullptr, 1234, (long long)numel, 0, s);
   ws.set_tail(ws.x, nullptr);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
@@ -753,7 +781,7 @@ void Engine::unet_forward(const float* cond, const float* x, float noise_level, 
                     T_("noise_level_mlp.3.weight"), T_("noise_level_mlp.3.bias"), wall_, ball_,
                     cfg_.inner_channel, noise_total_, table_};
   launch_noise_table(np, T_sched_, 1, s);
-  write_ctl(T_sched_, 0, nullptr, 0, 0, s);
+  write_ctl(T_sched_, 0, nullptr, 0, 0, 0, s);
   ws.set_tail(nullptr, ws.eps);
   run_ops(ws, s);
   ws.set_tail(ws.x, nullptr);
@@ -761,8 +789,8 @@ void Engine::unet_forward(const float* cond, const float* x, float noise_level, 
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
-void Engine::step(const float* cond, const float* x_t, const float* noise, int t, int B, int R, float* x_tm1,
-                  cudaStream_t s) {
+void Engine::step(const float* cond, const float* x_t, const float* noise, int t, int clip_denoised, int B, int R,
+                  float* x_tm1, cudaStream_t s) {
   CUDA_CHECK(cudaSetDevice(device_));
   REQUIRE(T_sched_ > 0, "step: no noise schedule installed (call b200sr3_set_schedule)");
   REQUIRE(t >= 0 && t < T_sched_, "step: t out of range");
@@ -773,21 +801,29 @@ void Engine::step(const float* cond, const float* x_t, const float* noise, int t
   last_total = last_conv = 0;
   if (cond) CUDA_CHECK(cudaMemcpyAsync(ws.cond, cond, img, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(ws.x, x_t, img, cudaMemcpyDeviceToDevice, s));
-  write_ctl(t, 3, noise, 0, (long long)(img / sizeof(float)), s);
+  write_ctl(t, 3, noise, 0, (long long)(img / sizeof(float)), 0, s, clip_denoised != 0);
   ws.set_tail(ws.x, nullptr);
   run_ops(ws, s);
   CUDA_CHECK(cudaMemcpyAsync(x_tm1, ws.x, img, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
-void Engine::sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int B, int R,
-                    float* out, float* snapshots, cudaStream_t s) {
+void Engine::philox_normal(uint64_t seed, int t, int64_t row_offset, int B, int R, float* out, cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  REQUIRE(out != nullptr && B >= 1 && R >= 1 && t >= 0 && row_offset >= 0, "philox_normal: bad argument");
+  launch_philox_fill(out, B, cfg_.out_channel, R, seed, t, row_offset, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void Engine::sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int64_t row_offset, int B,
+                    int R, float* out, float* snapshots, cudaStream_t s) {
   CUDA_CHECK(cudaSetDevice(device_));
   REQUIRE(T_sched_ > 0, "sample: no noise schedule installed (call b200sr3_set_schedule)");
   REQUIRE(noise_mode == B200SR3_NOISE_INJECTED || noise_mode == B200SR3_NOISE_PHILOX, "sample: bad noise_mode");
   REQUIRE(noise_mode != B200SR3_NOISE_INJECTED || noise != nullptr, "sample: injected mode needs a noise list");
   REQUIRE(out != nullptr, "sample: null output");
   REQUIRE(cond || !cfg_.conditional, "sample: cond is required for a conditional model");
+  REQUIRE(row_offset >= 0, "sample: row_offset must be >= 0");
   Workspace& ws = workspace(B, R);
   const int T = T_sched_;
   const size_t numel = (size_t)B * cfg_.out_channel * R * R;
@@ -800,9 +836,9 @@ void Engine::sample(const float* cond, int noise_mode, const float* noise, uint6
     CUDA_CHECK(cudaMemcpyAsync(ws.x, noise, img, cudaMemcpyDeviceToDevice, s));
   } else {
     // same generator as the update kernel, keyed at t = T (never a real step)
-    launch_philox_fill(ws.x, B, cfg_.out_channel, R, seed, T, s);
+    launch_philox_fill(ws.x, B, cfg_.out_channel, R, seed, T, row_offset, s);
   }
-  write_ctl(T - 1, noise_mode, noise, seed, (long long)numel, s);
+  write_ctl(T - 1, noise_mode, noise, seed, (long long)numel, row_offset, s);
   ws.set_tail(ws.x, nullptr);
   const int inter = 1 | (T / 10);
   int snap = 0;
@@ -823,7 +859,8 @@ void Engine::sample(const float* cond, int noise_mode, const float* noise, uint6
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
-void Engine::sample_host(const float* cond_host, uint64_t seed, int B, int R, float* out_host, cudaStream_t s) {
+void Engine::sample_host(const float* cond_host, uint64_t seed, int64_t row_offset, int B, int R, float* out_host,
+                         cudaStream_t s) {
   CUDA_CHECK(cudaSetDevice(device_));
   Workspace& ws = workspace(B, R);
   const size_t img = (size_t)B * cfg_.out_channel * R * R * sizeof(float);
@@ -831,18 +868,17 @@ void Engine::sample_host(const float* cond_host, uint64_t seed, int B, int R, fl
   REQUIRE(cond_host || !cfg_.conditional, "sample_host: cond is required for a conditional model");
   if (cond_host) CUDA_CHECK(cudaMemcpyAsync(ws.eps, cond_host, img, cudaMemcpyHostToDevice, s));
   // ws.eps doubles as the staging buffer: sample() copies cond -> ws.cond and out <- ws.x
-  sample(cond_host ? ws.eps : nullptr, B200SR3_NOISE_PHILOX, nullptr, seed, B, R, ws.eps, nullptr, s);
+  sample(cond_host ? ws.eps : nullptr, B200SR3_NOISE_PHILOX, nullptr, seed, row_offset, B, R, ws.eps, nullptr, s);
   CUDA_CHECK(cudaMemcpyAsync(out_host, ws.eps, img, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
 void Engine::layer_output(const std::string& layer, float* dst, int* C, int* H, int* W, cudaStream_t s) {
   CUDA_CHECK(cudaSetDevice(device_));
-  for (auto& kv : workspaces_) {
-    Workspace& ws = *kv.second;
+  for (auto wi = workspaces_.rbegin(); wi != workspaces_.rend(); ++wi) {      // most recently used plan first
+    Workspace& ws = **wi;
     auto it = ws.layer_out.find(layer);
     if (it == ws.layer_out.end()) continue;
-    // the most recently used workspace is not tracked; with one live (B,R) this is unambiguous
     const Act& a = it->second;
     if (C) *C = a.C;
     if (H) *H = a.H;

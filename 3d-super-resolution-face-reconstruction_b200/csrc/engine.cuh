@@ -40,6 +40,8 @@ struct PackedConv {     // weights of one tensor-core conv
   int taps = 9;         // main segment: 9 or 1
   int cin_main = 0;     // channels of the main source
   int c_res0 = 0, c_res1 = 0;   // folded 1x1 res_conv segments (0 = none)
+  bool res_identity = false;    // the 1x1 segment is an identity matrix (ResnetBlock with dim == dim_out, unet.py:101):
+                                // executed by the GEMM, but NOT a conv of the reference graph - no algorithmic FLOPs
   bool up_folded = false;       // [4*Cout][4*Cin]: parity 2x2 convs of Upsample(nearest 2x)+conv3x3
   float* bias = nullptr;        // static bias [Cout] (null when the bias comes from the table)
 };
@@ -49,7 +51,8 @@ struct Op {
   std::string name;
   bool is_conv = false;
   std::function<void(cudaStream_t)> run;
-  double flops = 0.0;   // algorithmic FLOPs (2*MAC on the reference graph) of one launch
+  double flops = 0.0;   // algorithmic FLOPs (2*MAC on the reference graph, SURVEY.md 8d) of one launch
+  double flops_executed = 0.0;   // what the tensor pipe runs: + identity-shortcut segments and K padding, - upsample folding
   double bytes = 0.0;   // algorithmic HBM bytes of one launch (HBM-bound kernels)
 };
 
@@ -91,11 +94,15 @@ class Engine {
 
   void unet_forward(const float* cond, const float* x, float noise_level, int B, int R, float* eps,
                     cudaStream_t s);
-  void step(const float* cond, const float* x_t, const float* noise, int t, int B, int R, float* x_tm1,
-            cudaStream_t s);
-  void sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int B, int R,
+  void step(const float* cond, const float* x_t, const float* noise, int t, int clip_denoised, int B, int R,
+            float* x_tm1, cudaStream_t s);
+  // row_offset: global index of batch row 0 (Philox counter), so shards / chunks of one logical batch draw the rows'
+  // own noise whatever the split
+  void sample(const float* cond, int noise_mode, const float* noise, uint64_t seed, int64_t row_offset, int B, int R,
               float* out, float* snapshots, cudaStream_t s);
-  void sample_host(const float* cond_host, uint64_t seed, int B, int R, float* out_host, cudaStream_t s);
+  void sample_host(const float* cond_host, uint64_t seed, int64_t row_offset, int B, int R, float* out_host,
+                   cudaStream_t s);
+  void philox_normal(uint64_t seed, int t, int64_t row_offset, int B, int R, float* out, cudaStream_t s);
   int num_snapshots() const;
   // One eager step with a CUDA event between consecutive launches: per-op device time.
   int profile_step(int B, int R, int max_ops, float* ms, double* flops, double* bytes, char* names,
@@ -112,7 +119,9 @@ class Engine {
   float* T_(const std::string& key) const;       // device pointer of a loaded tensor
   Workspace& workspace(int B, int R);
   void build_workspace(Workspace& ws);
-  void write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, cudaStream_t s);
+  void write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, long long row0, cudaStream_t s,
+                 bool clip = true);
+  void release();                                 // frees everything the engine owns (destructor, failed constructor)
   void run_ops(Workspace& ws, cudaStream_t s);
   void ensure_graph(Workspace& ws);
 
@@ -143,7 +152,10 @@ class Engine {
   bool use_halo_ = true;       // B200SR3_NO_HALO=1: first-generation conv + separate GroupNorm apply everywhere
   bool fuse_stats_ = true;     // B200SR3_NO_FUSED_STATS=1: GroupNorm statistics by chan_stats_kernel instead
 
-  std::map<std::pair<int, int>, std::unique_ptr<Workspace>> workspaces_;
+  // per-(B,R) workspaces, least recently used first; bounded (B200SR3_MAX_WORKSPACES, default 3): ragged last batches
+  // and varying evaluation batch sizes must not accumulate ~2 GB plans until cudaMalloc fails
+  std::vector<std::unique_ptr<Workspace>> workspaces_;
+  size_t max_workspaces_ = 3;
 };
 
 // Builds the launch closure of one tensor-core convolution (conv_umma.cu).

@@ -583,7 +583,8 @@ __global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
       }
     } else if (mode == 2) {
       const unsigned long long seed = t.ctl->seed;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+      const long long gpix = pix + t.ctl->row0 * (long long)R * R;      // keyed by the GLOBAL batch row
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)gpix, (uint32_t)(gpix >> 32), (uint32_t)ts, 0x5352u),
                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
       const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(128) tail_kernel(TailPlan t) {
 #pragma unroll
   for (int o = 0; o < OC; ++o) {
     const float xv = t.x[base + o * plane];
-    t.x[base + o * plane] = posterior_update(xv, acc[o], z[o], a, bc, c1, c2, sigma);
+    t.x[base + o * plane] = posterior_update(xv, acc[o], z[o], a, bc, c1, c2, sigma, t.ctl->no_clip ? __int_as_float(0x7f800000) : 1.0f);
   }
 }
 
@@ -664,14 +665,15 @@ __global__ void __launch_bounds__(256) tail_split_kernel(TailPlan t) {
       }
     } else if (mode == 2) {
       const unsigned long long seed = t.ctl->seed;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+      const long long gpix = pix + t.ctl->row0 * (long long)R * R;      // keyed by the GLOBAL batch row
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)gpix, (uint32_t)(gpix >> 32), (uint32_t)ts, 0x5352u),
                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
       const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
       const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
       z = zz[sub & 3];
     }
   }
-  t.x[idx] = posterior_update(t.x[idx], eps, z, a, bc, c1, c2, sigma);
+  t.x[idx] = posterior_update(t.x[idx], eps, z, a, bc, c1, c2, sigma, t.ctl->no_clip ? __int_as_float(0x7f800000) : 1.0f);
 }
 
 void launch_tail(const TailPlan& t, cudaStream_t s) {
@@ -702,12 +704,13 @@ void launch_tail(const TailPlan& t, cudaStream_t s) {
   CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void philox_fill_kernel(float* x, int B, int C, int R, unsigned long long seed, int t) {
+__global__ void philox_fill_kernel(float* x, int B, int C, int R, unsigned long long seed, int t, long long row0) {
   const long long npix = (long long)B * R * R;
   const size_t plane = (size_t)R * R;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (long long)gridDim.x * blockDim.x) {
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)t, 0x5352u),
+    const long long gpix = pix + row0 * (long long)plane;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)gpix, (uint32_t)(gpix >> 32), (uint32_t)t, 0x5352u),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
     const float zz[4] = {g0.x, g0.y, g1.x, g1.y};
@@ -716,11 +719,12 @@ __global__ void philox_fill_kernel(float* x, int B, int C, int R, unsigned long 
     for (int c = 0; c < C; ++c) x[base + c * plane] = zz[c & 3];
   }
 }
-void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, cudaStream_t s) {
+void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, long long row0, cudaStream_t s) {
+  REQUIRE(C >= 1 && C <= 4, "philox fill: one Philox block yields the (up to 4) channels of a pixel");
   const long long npix = (long long)B * R * R;
   long long blocks = (npix + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  philox_fill_kernel<<<(int)blocks, 256, 0, s>>>(x, B, C, R, seed, t);
+  philox_fill_kernel<<<(int)blocks, 256, 0, s>>>(x, B, C, R, seed, t, row0);
   CUDA_CHECK(cudaGetLastError());
 }
 

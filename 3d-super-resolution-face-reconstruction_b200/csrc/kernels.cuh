@@ -66,7 +66,8 @@ struct TailPlan {
 void launch_tail(const TailPlan& t, cudaStream_t s);
 void launch_ctl_advance(StepCtl* ctl, cudaStream_t s);
 // x[b][c][y][x] = N(0,1) from the same Philox stream the update kernel uses, keyed at step t
-void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, cudaStream_t s);
+// N(0,1) draws of the sampler's own stream at key t (t = T: x_T; t < T: z_t), rows [row0, row0 + B) of the global batch
+void launch_philox_fill(float* x, int B, int C, int R, unsigned long long seed, int t, long long row0, cudaStream_t s);
 
 // ---- standalone posterior update (kernel-level parity of diffusion.py:144-187 given eps)
 void launch_posterior_update(const float* x, const float* eps, const float* z, float a, float b,

@@ -31,7 +31,7 @@ extern "C" {
 #define B200SR3_API
 #endif
 
-#define B200SR3_ABI_VERSION 1
+#define B200SR3_ABI_VERSION 2
 #define B200SR3_MAX_LEVELS 8
 
 typedef struct b200sr3_handle b200sr3_handle;
@@ -95,26 +95,39 @@ B200SR3_API int b200sr3_set_schedule(b200sr3_handle* h, int T, const float* sqrt
 B200SR3_API int b200sr3_unet_forward(b200sr3_handle* h, const float* cond, const float* x, float noise_level,
                          int B, int R, float* eps, void* stream);
 
-/* Replaces GaussianDiffusion.p_sample(x, t, condition_x=cond) (diffusion.py:182-187) with
+/* Replaces GaussianDiffusion.p_sample(x, t, clip_denoised, condition_x=cond) (diffusion.py:182-187) with
  * the step's noise given (teacher-forced parity). `noise` may be NULL (treated as zeros; it is
- * ignored at t == 0 as in the reference). Device pointers. */
+ * ignored at t == 0 as in the reference). clip_denoised != 0 clamps x0 to [-1,1] (diffusion.py:175-176, the
+ * default and what p_sample_loop always uses); 0 leaves it unclamped. Device pointers. */
 B200SR3_API int b200sr3_step(b200sr3_handle* h, const float* cond, const float* x_t, const float* noise,
-                 int t, int B, int R, float* x_tm1, void* stream);
+                 int t, int clip_denoised, int B, int R, float* x_tm1, void* stream);
 
 /* Replaces GaussianDiffusion.p_sample_loop / super_resolution (diffusion.py:189-225), all T
  * steps, batched. out: fp32 [B,3,R,R] = x after t = 0. snapshots (optional): fp32
  * [n_snap,B,3,R,R], x after every t with t % (1 | T/10) == 0 in visiting order, which is what
  * `continous=True` concatenates after cond. noise_mode INJECTED reads `noise` (T*B*3*R*R
- * floats); PHILOX ignores it and uses `seed`. Device pointers. */
+ * floats); PHILOX ignores it and uses `seed`. Device pointers.
+ * `row_offset` (PHILOX): global index of this call's batch row 0. The stream is keyed by (seed, t, GLOBAL row, y, x),
+ * so a face's noise - like the reference's per-image torch.randn draws - does not depend on how one logical batch is
+ * sharded over GPUs or chunked over calls: rank g of a sharded run passes its shard start, a chunked caller passes the
+ * chunk start, and all of them pass the same seed. 0 for a stand-alone batch. */
 B200SR3_API int b200sr3_sample(b200sr3_handle* h, const float* cond, int noise_mode, const float* noise,
-                   uint64_t seed, int B, int R, float* out, float* snapshots, void* stream);
+                   uint64_t seed, int64_t row_offset, int B, int R, float* out, float* snapshots, void* stream);
 B200SR3_API int b200sr3_num_snapshots(b200sr3_handle* h);
+
+/* The sampler's own N(0,1) stream, as the PHILOX mode of b200sr3_sample draws it: out fp32 [B,out_channel,R,R] =
+ * the draw keyed (seed, t, rows row_offset .. row_offset+B-1). t = T (the schedule length) is x_T, the
+ * `torch.randn(shape)` of diffusion.py:205 (:196 unconditional); 0 < t < T is z_t, the `torch.randn_like(x)` of
+ * diffusion.py:186. Used by the statistical tests of the stream and to return x_T where the reference does
+ * (unconditional continous=True, diffusion.py:195-196). Device pointer. */
+B200SR3_API int b200sr3_philox_normal(b200sr3_handle* h, uint64_t seed, int t, int64_t row_offset, int B, int R,
+                   float* out, void* stream);
 
 /* The same call for HOST buffers (the end-to-end path bench.py times as `e2e`): cond is copied
  * host->device, the chain runs with PHILOX noise, out is copied device->host, and the call
  * returns after the copy has completed. cond/out should be pinned for full PCIe speed. */
-B200SR3_API int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int B, int R,
-                        float* out_host, void* stream);
+B200SR3_API int b200sr3_sample_host(b200sr3_handle* h, const float* cond_host, uint64_t seed, int64_t row_offset,
+                        int B, int R, float* out_host, void* stream);
 
 /* Introspection for layer-level parity tests: copy the activation a named layer produced in
  * the most recent forward ("downs.0" ... "ups.18", "mid.0", "mid.1"; unet.py module names) to

@@ -160,13 +160,15 @@ def unet_forward(sd, model_opt, x, noise_level, taps=None):
 
 
 # ----------------------------------------------------------------------------- sampler
-def p_sample(sd, model_opt, tabs, x, t, cond, noise):
-    """One reverse step, diffusion.py:164-187. `noise` is z_t (ignored at t == 0)."""
+def p_sample(sd, model_opt, tabs, x, t, cond, noise, clip_denoised=True):
+    """One reverse step, diffusion.py:164-187. `noise` is z_t (ignored at t == 0); cond None = the unconditional
+    branch (diffusion.py:172-173: the UNet sees x alone)."""
     b = x.shape[0]
     nl = torch.FloatTensor([tabs["sqrt_ac_prev"][t + 1]]).repeat(b, 1)
-    eps = unet_forward(sd, model_opt, torch.cat([cond, x], dim=1), nl)
+    eps = unet_forward(sd, model_opt, torch.cat([cond, x], dim=1) if cond is not None else x, nl)
     x0 = tabs["sqrt_recip_ac"][t] * x - tabs["sqrt_recipm1_ac"][t] * eps
-    x0.clamp_(-1.0, 1.0)
+    if clip_denoised:
+        x0.clamp_(-1.0, 1.0)
     mean = tabs["coef1"][t] * x0 + tabs["coef2"][t] * x
     z = noise if t > 0 else torch.zeros_like(x)
     return mean + z * (0.5 * tabs["post_logvar"][t]).exp()
@@ -174,16 +176,17 @@ def p_sample(sd, model_opt, tabs, x, t, cond, noise):
 
 @torch.no_grad()
 def sample_loop(sd, model_opt, tabs, cond, noise, record=None, t_stop=0):
-    """diffusion.py:189-215, conditional branch, with the noise list injected.
+    """diffusion.py:189-215 with the noise list injected.
 
     noise[0] is x_T, noise[T - t] is z_t for t >= 1. Returns (final x [B,3,R,R], snapshots
-    as in `continous=True`: cat([cond, x at every t % (1 | T//10) == 0])).
+    as in `continous=True`: cat([cond, x at every t % (1 | T//10) == 0]); with cond None (unconditional branch,
+    diffusion.py:193-200) the list starts with x_T instead).
     `record(t, x_t, x_tm1)` is called after every step; t_stop > 0 truncates the chain.
     """
     T = tabs["T"]
     inter = 1 | (T // 10)
     x = noise[0]
-    ret = cond
+    ret = cond if cond is not None else x
     for t in reversed(range(t_stop, T)):
         x_new = p_sample(sd, model_opt, tabs, x, t, cond, noise[T - t] if t > 0 else None)
         if record is not None:

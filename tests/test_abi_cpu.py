@@ -20,7 +20,10 @@ def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.b200sr3_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "b200sr3.h")).read()
+    declared_version = int(re.search(r"#define\s+B200SR3_ABI_VERSION\s+(\d+)", header).group(1))
+    from b200sr3 import _lib
+    assert lib.b200sr3_abi_version() == declared_version == _lib.ABI_VERSION
 
 
 def test_library_has_blackwell_code(built_lib):

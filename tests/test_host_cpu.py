@@ -118,3 +118,28 @@ def test_product_never_touches_the_oracle():
                         if re.search(r"^\s*(from|import)\s+oracle\b", line) or re.search(r"[\"']\S*oracle/", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_define_G_accepts_every_reference_yaml():
+    """the replacement factory takes the UNMODIFIED reference YAMLs (config/sr_sr3_VGGF2_*.yml).
+    The YAML files live in the reference checkout, which only exists in the build container."""
+    import glob
+    ref = os.environ.get("B200SR3_REF", "/root/reference")
+    files = sorted(glob.glob(os.path.join(ref, "config", "sr_sr3_VGGF2_*.yml")))
+    if not files:
+        pytest.skip("reference checkout not present")
+    assert len(files) >= 20
+    for path in files:
+        opt = b200sr3.configs.load_yaml(path)
+        net = b200sr3.define_G(opt)
+        assert sum(p.numel() for p in net.parameters()) == 92556931, path
+        sched = opt["sr"]["model"]["beta_schedule"]["val"]
+        net.set_new_noise_schedule(sched, [torch.device("cpu")])
+        name = os.path.basename(path)[:-4]
+        parts = name.split("_")
+        if parts[3].isdigit():          # (sr_sr3_VGGF2_test_code.yml names no resolution pair)
+            assert net.num_timesteps == b200sr3.configs.TIMESTEPS[(int(parts[3]), int(parts[4]))], name
+            mine = b200sr3.configs.named("_".join(parts[:6]))["sr"]["model"]
+            assert mine["unet"]["channel_multiplier"] == list(opt["sr"]["model"]["unet"]["channel_multiplier"])
+            assert mine["diffusion"] == dict(opt["sr"]["model"]["diffusion"])
+        del net

@@ -1,13 +1,15 @@
 """The CPU oracle against the vectors the REAL reference produced (oracle/make_golden.py)."""
+import hashlib
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import synthetic_weights
 from oracle import sr3_oracle as O
 from oracle.make_golden import TOL_CHAIN, TOL_STEP, model_opt
-from oracle.weights import state_dict_digest
+from oracle.weights import make_inputs, state_dict_digest
 
 
 def _load(golden_dir, name):
@@ -69,3 +71,26 @@ def test_free_running_chain_matches_reference(golden_dir):
     assert float((snaps - torch.from_numpy(g["snapshots"])).abs().max()) <= TOL_CHAIN
     assert float((fin[-1] - torch.from_numpy(g["last"])).abs().max()) <= TOL_CHAIN   # continous=False quirk
     assert O.psnr_uint8(fin[0], torch.from_numpy(g["xs"][-1][0])) > 80.0
+
+
+@pytest.mark.parametrize("fname", ["chain_r64_T200.npz", "chain_r128_T600.npz"])
+def test_headline_chain_steps_match_reference(golden_dir, fname):
+    """Cases E / F (oracle/make_golden_headline.py): the oracle reproduces x_{t-1} of the unmodified reference's own
+    full-T chains of the headline configs (16->128 T=600, 16->64 T=200) at the first step and at t = 0."""
+    g = _load(golden_dir, fname)
+    T, R, B = int(g["T"]), int(g["R"]), int(g["B"])
+    sd = synthetic_weights(int(g["weight_seed"]), float(g["weight_gain"]))
+    assert state_dict_digest(sd) == str(g["weight_sha256"])
+    cond, noise = make_inputs(B, R, T, seed=int(g["input_seed"]))
+    assert np.array_equal(cond.numpy(), g["cond"])
+    assert hashlib.sha256(noise.numpy().tobytes()).hexdigest() == str(g["noise_sha256"])     # PCG64 stream is portable
+    mopt = model_opt(T)
+    tabs = O.schedule_tables(mopt["beta_schedule"]["val"])
+    state = {0: noise[0]}
+    state.update({int(k): torch.from_numpy(x) for k, x in zip(g["keep_k"], g["xs"])})
+    assert np.array_equal(g["xs"][-1], g["final"])
+    for t in (T - 1, 0):
+        z = noise[T - t] if t > 0 else torch.zeros_like(cond)
+        with torch.no_grad():
+            out = O.p_sample(sd, mopt, tabs, state[T - 1 - t], t, cond, z)
+        assert float((out - state[T - t]).abs().max()) <= TOL_STEP, (fname, t)

@@ -1,4 +1,5 @@
-"""Multi-GPU path on CPU: world_size-2 gloo, contiguous batch split, one final gather."""
+"""Multi-GPU path on CPU: world_size-2 gloo, contiguous batch split, one final gather (a shared host buffer:
+no collective library on the data path; torch.distributed only carries rank/world and the control barrier)."""
 import os
 import socket
 
@@ -34,6 +35,25 @@ def _worker(rank, world, port, batch, q):
     local = sharded_sample(fake_sampler, cond, noise, gather=False)
     lo, hi = shard_bounds(batch, rank, world)
     ok = torch.equal(full, cond * 2 + noise[0]) and torch.equal(local, (cond * 2 + noise[0])[lo:hi]) and seen[0] == hi - lo
+    # a sampler that draws its own noise is told its slice's global start row (the Philox row offset)
+    rows = []
+
+    def row_sampler(c, z, row_offset):
+        rows.append(row_offset)
+        return c + row_offset
+
+    full2 = sharded_sample(row_sampler, cond, None)
+    want = torch.cat([cond[a:b] + a for a, b in (shard_bounds(batch, r, world) for r in range(world))])
+    ok = ok and rows == [lo] and torch.equal(full2, want)
+    # a persistent gather buffer reused over several chains (what bench.py does), no barrier between puts
+    from b200sr3.sharding import HostGather
+    hg = HostGather((batch, 3, 4, 4), pin=False)
+    for k in range(3):
+        hg.put(lo, cond[lo:hi] * (k + 1))
+    hg.wait()
+    ok = ok and torch.equal(hg.full(), cond * 3)
+    hg.wait()
+    hg.close()
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
