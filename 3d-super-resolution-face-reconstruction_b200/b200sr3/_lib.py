@@ -45,7 +45,8 @@ _SIGNATURES = {
     "b200sr3_layer_output": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
     "b200sr3_last_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200sr3_profile_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
-                                       C.POINTER(C.c_double), C.c_char_p, C.c_int, C.POINTER(C.c_int), _P]),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_int,
+                                       C.POINTER(C.c_int), _P]),
     "b200sr3_conv2d": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float), _P]),
     "b200sr3_conv_block": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int,

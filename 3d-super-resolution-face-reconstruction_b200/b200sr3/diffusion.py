@@ -374,19 +374,20 @@ class GaussianDiffusion(nn.Module):
         return out_host
 
     def profile_step(self, B, R):
-        """Per-launch device times of one sampling step: list of (name, ms, flops, bytes)."""
+        """Per-launch device times of one sampling step: list of (name, ms, flops, bytes, flops_executed)."""
         eng = self._engine()
         n_max = 1024
         ms = (C.c_float * n_max)()
         fl = (C.c_double * n_max)()
+        fx = (C.c_double * n_max)()
         by = (C.c_double * n_max)()
         names = C.create_string_buffer(64 * n_max)
         n = C.c_int()
         with torch.cuda.device(self._sampling_device()):
-            _lib.check(eng.lib.b200sr3_profile_step(eng.handle, B, R, n_max, ms, fl, by, names, len(names),
+            _lib.check(eng.lib.b200sr3_profile_step(eng.handle, B, R, n_max, ms, fl, fx, by, names, len(names),
                                                     C.byref(n), _stream()))
         nm = names.value.decode().split("\n")
-        return [(nm[i], ms[i], fl[i], by[i]) for i in range(n.value)]
+        return [(nm[i], ms[i], fl[i], by[i], fx[i]) for i in range(n.value)]
 
     def layer_output(self, name):
         """Activation of a UNet module ('downs.3', 'mid.0', ...) from the most recent forward."""

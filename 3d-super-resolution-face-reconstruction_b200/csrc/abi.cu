@@ -138,11 +138,11 @@ int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int64_t* conv) 
   });
 }
 
-int b200sr3_profile_step(b200sr3_handle* h, int B, int R, int max_ops, float* ms, double* flops, double* bytes,
-                         char* names, int names_len, int* n_ops, void* stream) {
+int b200sr3_profile_step(b200sr3_handle* h, int B, int R, int max_ops, float* ms, double* flops, double* flops_executed,
+                         double* bytes, char* names, int names_len, int* n_ops, void* stream) {
   return guarded([&] {
     REQUIRE(ms && n_ops, "profile_step: null argument");
-    *n_ops = E(h).profile_step(B, R, max_ops, ms, flops, bytes, names, names_len, (cudaStream_t)stream);
+    *n_ops = E(h).profile_step(B, R, max_ops, ms, flops, flops_executed, bytes, names, names_len, (cudaStream_t)stream);
   });
 }
 
@@ -268,7 +268,7 @@ int b200sr3_conv2d(int device, const float* x, const float* w, const float* bias
 int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int C1, const float* gamma,
                        const float* beta, int groups, int swish, const float* w, const float* bias, const float* r0,
                        int Cr0, const float* r1, int Cr1, const float* wres, int B, int H, int W, int Cout,
-                       int upsample2x, float* y, float* stats_out, int iters, float* avg_ms, void* stream) {
+                       int resample, float* y, float* stats_out, int iters, float* avg_ms, void* stream) {
   return guarded([&] {
     REQUIRE(x0 && w && y, "conv_block: null pointer");
     REQUIRE((x1 != nullptr) == (C1 > 0) && (r0 != nullptr) == (Cr0 > 0) && (r1 != nullptr) == (Cr1 > 0),
@@ -295,10 +295,14 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       std::vector<void*>& v;
       ~Cleanup() { for (void* p : v) cudaFree(p); }
     } cleanup{tmp};
-    const bool up = upsample2x != 0;
-    REQUIRE(conv_halo_eligible(H, W, (C0 % 64 == 0) && (C1 % 64 == 0) && (Cr0 % 64 == 0) && (Cr1 % 64 == 0), Cout),
+    REQUIRE(resample >= 0 && resample <= 2, "conv_block: resample is 0 (none), 1 (nearest 2x up) or 2 (stride 2)");
+    const bool up = resample == 1, down = resample == 2;
+    REQUIRE(!down || (H % 2 == 0 && W % 2 == 0), "conv_block: a stride-2 conv needs even H and W");
+    const int TH = down ? H / 2 : H, TW = down ? W / 2 : W;      // the grid the tiles walk
+    REQUIRE(conv_halo_eligible(TH, TW, (C0 % 64 == 0) && (C1 % 64 == 0) && (Cr0 % 64 == 0) && (Cr1 % 64 == 0), Cout),
             "conv_block: shape not supported by the halo conv (H % 16, W % 8, W >= 16, channels % 64)");
     REQUIRE(!up || (Cr0 + Cr1 == 0), "conv_block: a folded upsample has no shortcut");
+    REQUIRE(!down || (Cr0 + Cr1 + C1 == 0 && gamma == nullptr), "conv_block: a stride-2 conv is one raw source");
 
     auto make_act = [&](const float* src, int C, bool want_stats) {
       Act a;
@@ -342,7 +346,7 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       else gn_in_kernel = true;                                      // default: the conv builds the table itself
     }
     Act out;
-    out.B = B; out.C = Cout; out.H = up ? 2 * H : H; out.W = up ? 2 * W : W;
+    out.B = B; out.C = Cout; out.H = up ? 2 * H : TH; out.W = up ? 2 * W : TW;
     out.ptr = (bf16*)dalloc(out.elems() * sizeof(bf16));
     PackedConv pc;
     const int cin = C0 + C1;
@@ -352,6 +356,11 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       pc.k_total = 4 * cin;
       pc.w = (bf16*)dalloc((size_t)4 * Cout * pc.k_total * sizeof(bf16));
       launch_pack_upfold_weight(w, pc.w, Cout, cin, cin, s);
+    } else if (down) {
+      pc.down_perm = true;
+      pc.k_total = 9 * cin;
+      pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
+      pack_conv_weight_by_input_parity(w, pc.w, Cout, cin, s);
     } else {
       pc.k_total = 9 * cin + Cr0 + Cr1;
       pc.w = (bf16*)dalloc((size_t)Cout * pc.k_total * sizeof(bf16));
@@ -376,7 +385,8 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 16 * sizeof(unsigned long long)));
     }
     Op op = make_conv_halo_op("conv_block", srcs, up, pc, bias, 0, nullptr, out, gn, cin, swish != 0,
-                              (stats_out || timing) ? &st : nullptr, nullptr, nullptr, gn_in_kernel ? &gplan : nullptr);
+                              (stats_out || timing) ? &st : nullptr, nullptr, nullptr, gn_in_kernel ? &gplan : nullptr,
+                              down ? 2 : 1);
     op.run(s);
     launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
     CUDA_CHECK(cudaStreamSynchronize(s));

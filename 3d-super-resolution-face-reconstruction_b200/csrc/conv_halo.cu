@@ -105,10 +105,17 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
-                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats) {
+                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats, int stride) {
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
-  const int PH = a0.H, PW = a0.W;
+  REQUIRE(stride == 1 || stride == 2, "halo conv: stride 1 or 2");
+  // stride 2 (Downsample, unet.py:68-74): the tiles walk the OUTPUT grid and the input is read through its four
+  // (row parity, column parity) sub-grids, each a strided view with its own tensor map - see the segment list below
+  REQUIRE(stride == 1 || (srcs.size() == 1 && srcs[0].ntaps == 9 && srcs[0].gn_off < 0 && !upsample2x && !tail &&
+                          a0.H % 2 == 0 && a0.W % 2 == 0 && w.down_perm),
+          "halo conv: a stride-2 conv is one raw 3x3 source with parity-ordered weights");
+  REQUIRE(stride == 2 || !w.down_perm, "halo conv: parity-ordered weights belong to a stride-2 conv");
+  const int PH = a0.H / stride, PW = a0.W / stride;
   auto pp = std::make_shared<ConvHaloParams>();
   ConvHaloParams& p = *pp;
   memset(&p, 0, sizeof(p));
@@ -135,14 +142,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   const int main_taps = upsample2x ? 4 : 9;
   int c_seen = 0, k_short = main_taps * c_main, kblocks = 0;
   bool any_gn = false;
-  for (size_t i = 0; i < srcs.size(); ++i) {
-    const HaloSource& s = srcs[i];
-    const Act& a = s.act;
-    REQUIRE(a.B == out.B && a.H == PH && a.W == PW && a.C % CONV_BLOCK_K == 0, "halo conv: source shape mismatch");
-    REQUIRE(s.ntaps == 9 || s.ntaps == 1, "halo conv: a source is 3x3 or 1x1");
-    REQUIRE(!(upsample2x && s.ntaps == 1), "halo conv: a folded upsample has no shortcut");
-    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-    cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W * a.C * 2, (cuuint64_t)a.H * a.W * a.C * 2};
+  // tensor map of one source view: (C, Wd, Hd, B) with the given pixel strides, box = the geometry's halo
+  auto encode_src = [&](int mi, const bf16* base, int C, int Wd, int Hd, size_t sW, size_t sH, size_t sB) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)a0.B};
+    cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sB * 2};
     cuuint32_t box[4] = {(cuuint32_t)CONV_BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
     if (g2) {             // natural order, box = the 5 x 5 grids (top zero row, left zero column) of five images
       box[1] = 5; box[2] = 5; box[3] = 5;
@@ -152,9 +155,42 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       box[2] = 2; box[3] = 10;
     }
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode_tiled(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.ptr, dims, strides, box, estr,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    CUresult r = encode_tiled(&p.a_map[mi], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(halo) failed with CUresult " + std::to_string((int)r));
+  };
+  const int pitch = g2 ? 5 : (geo1(PH, PW) ? 20 : HALO_W);      // pixels per halo-tile row (HaloGeo<GEO>::PITCH)
+  if (stride == 2) {
+    // Output (oy, ox) reads input (2 oy + ky - 1, 2 ox + kx - 1): ky = 1 is row oy of the even-row view, ky = 0 / 2 are
+    // rows oy - 1 / oy of the odd-row view, likewise in x. So the conv is four small convs over the parity views, whose
+    // taps are 2x2 / 1x2 / 2x1 / 1x1 windows of the usual halo tile (top-left corner = view pixel (oy-1, ox-1)); the
+    // view's coordinate -1 is the conv's zero padding (TMA zero fill). Weights arrive parity-ordered (PackedConv::down_perm):
+    // taps (0,0) (0,2) (2,0) (2,2) | (1,0) (1,2) | (0,1) (2,1) | (1,1).
+    const Act& a = a0;
+    REQUIRE(a.B == out.B && a.C % CONV_BLOCK_K == 0 && a.C == w.cin_main, "halo conv: source shape mismatch");
+    static const int S2[4][4] = {{1, 1, 4, 2}, {0, 1, 2, 2}, {1, 0, 2, 1}, {0, 0, 1, 1}};      // row parity, col parity, taps, taps per row
+    const int pix0[4] = {0, pitch, 1, pitch + 1};
+    int tap0 = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int py = S2[i][0], px = S2[i][1];
+      encode_src(i, a.ptr + ((size_t)py * a.W + px) * a.C, a.C, PW, PH, (size_t)2 * a.C, (size_t)2 * a.W * a.C,
+                 (size_t)a.H * a.W * a.C);
+      HaloSeg& sg = p.seg[i];
+      sg.map = i; sg.cblocks = a.C / CONV_BLOCK_K; sg.gn_off = -1;
+      sg.ntaps = S2[i][2]; sg.tap_w = S2[i][3]; sg.pix0 = pix0[i];
+      sg.k_base = tap0 * a.C; sg.k_tap_stride = a.C;
+      tap0 += sg.ntaps;
+    }
+    k_short = 9 * a.C;
+    p.num_segs = 4;
+  } else
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    const HaloSource& s = srcs[i];
+    const Act& a = s.act;
+    REQUIRE(a.B == out.B && a.H == PH && a.W == PW && a.C % CONV_BLOCK_K == 0, "halo conv: source shape mismatch");
+    REQUIRE(s.ntaps == 9 || s.ntaps == 1, "halo conv: a source is 3x3 or 1x1");
+    REQUIRE(!(upsample2x && s.ntaps == 1), "halo conv: a folded upsample has no shortcut");
+    encode_src((int)i, a.ptr, a.C, a.W, a.H, (size_t)a.C, (size_t)a.W * a.C, (size_t)a.H * a.W * a.C);
     HaloSeg& sg = p.seg[i];
     sg.map = (int)i;
     sg.cblocks = a.C / CONV_BLOCK_K;
@@ -163,11 +199,15 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       REQUIRE(k_short == main_taps * c_main && kblocks == (c_seen / CONV_BLOCK_K) * main_taps,
               "halo conv: main sources must come first");
       sg.ntaps = main_taps;
+      sg.tap_w = upsample2x ? 2 : 3;
+      sg.pix0 = upsample2x ? -1 : 0;      // folded upsample: the 2x2 window depends on the output parity
       sg.k_base = c_seen;
       sg.k_tap_stride = c_main;
       c_seen += a.C;
     } else {
       sg.ntaps = 1;
+      sg.tap_w = 1;
+      sg.pix0 = pitch + 1;                // centre pixel
       sg.k_base = k_short;
       sg.k_tap_stride = 0;
       k_short += a.C;
@@ -177,7 +217,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     if (s.gn_off >= 0)
       REQUIRE((gn != nullptr || gn_from_stats != nullptr) && s.gn_off + a.C <= gn_C, "halo conv: GroupNorm table too small");
   }
-  p.num_segs = (int)srcs.size();
+  if (stride == 1) p.num_segs = (int)srcs.size();
   REQUIRE(k_short == w.k_total, "halo conv: packed weight K does not match the segment list");
   REQUIRE(w.up_folded == upsample2x, "halo conv: weight packing / upsample mismatch");
   p.tiles_w = g1 ? 1 : PW / HALO_TW;
@@ -309,7 +349,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   {
     const double m = (double)out.B * out.H * out.W;
     double k = 0, k_exec = 0;
-    for (const HaloSource& s : srcs) {
+    for (const HaloSource& s : srcs) {      // (a stride-2 conv has one 9-tap source: 9 C either way)
       // reference graph: full 3x3 at output resolution; a res_conv segment counts, an identity shortcut
       // that merely rides the GEMM (unet.py:101, nn.Identity) does not
       if (!(s.ntaps == 1 && w.res_identity)) k += (double)s.ntaps * s.act.C;

@@ -83,10 +83,16 @@ template <> struct HaloGeo<2> {
 struct HaloSeg {
   int map;           // a_map index
   int cblocks;       // 64-channel blocks of this source
-  int ntaps;         // 9: 3x3; 4: parity 2x2 of a folded upsample; 1: 1x1 shortcut (centre pixel)
+  int ntaps;         // 9: 3x3; 4: parity 2x2 of a folded upsample; 1: 1x1 shortcut (centre pixel); 4/2/2/1: the four
+                     // input-parity views of a stride-2 conv (unet.py:68-74)
   int k_base;        // K column of (tap 0, block 0) in the packed weights
   int k_tap_stride;  // K columns between consecutive taps
   int gn_off;        // channel offset of this source in the GN table; < 0: raw input, no transform
+  // the taps' windows into the halo tile: tap i reads the window that starts at pixel pix0 + (i / tap_w) * PITCH + i % tap_w
+  // (pixel 0 = the halo's top-left corner, i.e. filter tap (0,0) of a 3x3). pix0 < 0: the folded upsample, whose 2x2
+  // window depends on the tile's output parity.
+  int tap_w;
+  int pix0;
 };
 
 struct alignas(64) ConvHaloParams {
@@ -123,6 +129,13 @@ struct alignas(64) ConvHaloParams {
   // BLOCK_N == 16 ("tail"): the conv is final_conv (unet.py:233, Cout = out_channel <= 4 padded to 16) and
   // the epilogue applies the sampler update (diffusion.py:144-187) to the fp32 NCHW state instead of
   // storing an activation: eps -> x0 = clamp(A x - B eps) -> mean -> + sigma z.
+  // HEAD (template flag): the conv is downs.0 (unet.py:187, in_channel -> inner_channel) and its A operand never exists
+  // in HBM: the transform warps read the fp32 NCHW sampler inputs cat([cond, x], 1) (diffusion.py:170) for the halo
+  // pixels themselves and write the split-precision bf16 rows (hi | lo | hi, see launch_pack_head_split_weight)
+  // straight into the swizzled tile. No TMA load, no 64-channel padded operand in memory.
+  const float* head_cond;          // fp32 NCHW [B][head_cc][H][W] or null
+  const float* head_x;             // fp32 NCHW [B][head_cx][H][W]
+  int head_cc, head_cx;            // head_cc + head_cx <= 8
   float* tail_x;                   // fp32 NCHW [B][tail_oc][H][W], updated in place (null: eps only)
   float* tail_eps;                 // optional fp32 NCHW eps output
   const float* coefs;              // [5][T]: A, Bc, C1, C2, LV
@@ -378,12 +391,14 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
 // per MMA from (4 + N/32) KB to (4 + N/64) KB. The leader (rank 0) issues the MMAs; its barriers collect both CTAs'
 // weight loads (TMA in cta_group::2 form signals the leader's barrier), transform arrivals and epilogue releases;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
-template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1>
+template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = false>
 __global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   using S = HaloSmem<BLOCK_N, MT, GEO, CG>;
   static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
-  constexpr bool XF = FUSE_GN || CG == 2;      // transform warps active (in a pair they also forward "halo landed" to the leader)
+  static_assert(!HEAD || (!FUSE_GN && GEO == 0 && CG == 1 && BLOCK_N == 64), "the head conv is a raw 3x3, Cout = 64");
+  constexpr bool XF = FUSE_GN || CG == 2 || HEAD;      // transform warps active (in a pair they also forward "halo landed" to the leader)
+  constexpr int KSTEPS = HEAD ? 2 : 4;         // K = 16 steps per 64-channel block: the head's split operand fills 3 * 8 <= 32 channels
   using G = HaloGeo<GEO>;
   static_assert(GEO == 0 || (BLOCK_N != 16 && MT == 1), "the multi-image geometries run plain convs, one tile at a time");
   static_assert(GEO != 2 || BLOCK_N == 64, "the 4x4 geometry runs BLOCK_N = 64");
@@ -475,6 +490,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   // kernel takes ~3 k cycles (caches and TLBs start cold at every launch) and used to begin after ~2 k cycles of setup.
   // One halo stage = the MT tiles' boxes of one 64-channel block, all completing on a_full(stage).
   auto issue_halo = [&](int stage, int map, int cb, const Tile* t) {
+    if (HEAD) {      // nothing to fetch: "full" only says that the slot is free for the transform warps to fill
+      ptx::mbar_arrive(a_full(stage));
+      return;
+    }
     ptx::mbar_expect_tx(a_full(stage), HALO_ABLATE(8) ? 0 : MT * G::BYTES);
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
@@ -680,8 +699,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         uint32_t accum = 0;
         for (int sg = 0; sg < p.num_segs; ++sg) {
           const int ntaps = p.seg[sg].ntaps, cblocks = p.seg[sg].cblocks;
-          const int ntx = ntaps == 9 ? 3 : (ntaps == 4 ? 2 : 1);
-          const uint32_t pix0 = ntaps == 9 ? 0u : (ntaps == 4 ? (uint32_t)((par >> 1) * G::PITCH + (par & 1)) : (uint32_t)(G::PITCH + 1));
+          const int ntx = p.seg[sg].tap_w;
+          const uint32_t pix0 = p.seg[sg].pix0 >= 0 ? (uint32_t)p.seg[sg].pix0 : (uint32_t)((par >> 1) * G::PITCH + (par & 1));
           for (int cb = 0; cb < cblocks; ++cb) {
             HDBG_T0();
             ptx::mbar_wait(XF ? a_ready(as) : a_full(as), aphase);
@@ -706,7 +725,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KSTEPS; ++k) {
                   if (CG == 2)
                     umma_bf16_pair(d_tmem + (uint32_t)(m * BLOCK_N), desc(a_lo + (uint32_t)(m * (G::STRIDE >> 4) + 2 * k), A_HI),
                                    desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
@@ -1063,6 +1082,53 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           HDBG_ACC(0);
           if (HALO_DBG && tt == 0 && !first_halo_seen) { first_halo_seen = true; p.dbg[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_entry); }   // [7] first halo landed
           HDBG_T0();
+          if (HEAD) {
+            // one halo pixel per thread (180 of the 256): the pixel's fp32 inputs (cond channels, then x channels) -> a
+            // 64-byte split-precision row hi | lo | hi; out-of-image pixels are the conv's zero padding. All loads of the
+            // MT tiles are issued before any arithmetic.
+            const int n = p.head_cc + p.head_cx;
+            const size_t plane = (size_t)p.H * p.W;
+            float v[MT][8];
+            const int hy = tt / G::PITCH, hx = tt - hy * G::PITCH;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              const int gy = t[m].y0 - 1 + hy, gx = t[m].x0 - 1 + hx;
+              const bool ok = tt < G::NPIX && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+              const size_t off = (size_t)gy * p.W + gx;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                v[m][c] = 0.f;
+                if (ok && c < n)
+                  v[m][c] = c < p.head_cc ? __ldg(p.head_cond + ((size_t)t[m].b * p.head_cc + c) * plane + off)
+                                          : __ldg(p.head_x + ((size_t)t[m].b * p.head_cx + (c - p.head_cc)) * plane + off);
+              }
+            }
+            if (tt < G::NPIX) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                float row[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) row[i] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  // slots c, n + c, 2n + c with run-time n: selects over the unrolled row (no local-memory indexing)
+                  const float hi = __bfloat162float(__float2bfloat16_rn(v[m][c]));
+                  const float lo = v[m][c] - hi;
+#pragma unroll
+                  for (int i = 0; i < 24; ++i) {
+                    if (c < n && i == c) row[i] = hi;
+                    if (c < n && i == n + c) row[i] = lo;
+                    if (c < n && i == 2 * n + c) row[i] = hi;
+                  }
+                }
+                uint8_t* dst = smem_gen + as * S::A_STAGE + m * G::STRIDE + tt * 128;
+#pragma unroll
+                for (int jj = 0; jj < 2 * KSTEPS; ++jj)
+                  *reinterpret_cast<uint4*>(dst + ((jj ^ (tt & 7)) << 4)) = pack8(row + 8 * jj);
+              }
+            }
+            fence_proxy_async_smem();
+          }
           if (seg.gn_off >= 0 && !HALO_ABLATE(2)) {
 #pragma unroll
             for (int m = 0; m < MT; ++m) {

@@ -18,25 +18,33 @@ static void add_vec(const float* a, const float* b, float* o, int n, cudaStream_
   add_vec_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, o, n);
   CUDA_CHECK(cudaGetLastError());
 }
-// OIHW fp32 (channel slice [c0, c0+cseg) of cin_total) -> packed bf16 K-major row segment.
+// OIHW fp32 (channel slice [c0, c0+cseg) of cin_total) -> packed bf16 K-major row segment. K position `tap` holds filter
+// tap order.t[tap] (identity for every conv but the parity-ordered stride-2 ones).
+struct TapOrder { int t[9]; };
+static const TapOrder TAPS_NATURAL = {{0, 1, 2, 3, 4, 5, 6, 7, 8}};
+static const TapOrder TAPS_BY_INPUT_PARITY = {{0, 2, 6, 8, 3, 5, 1, 7, 4}};      // PackedConv::down_perm
 __global__ void pack_slice_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int cseg, int c0,
-                                  int cin_total, int taps, int cpad, int k_off, int k_total) {
+                                  int cin_total, int taps, int cpad, int k_off, int k_total, TapOrder order) {
   const long long total = (long long)Cout * taps * cpad;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % cpad);
     const int tap = (int)((idx / cpad) % taps);
     const int o = (int)(idx / ((long long)cpad * taps));
-    const float v = (c < cseg) ? src[((size_t)o * cin_total + c0 + c) * taps + tap] : 0.f;
+    const float v = (c < cseg) ? src[((size_t)o * cin_total + c0 + c) * taps + order.t[tap]] : 0.f;
     dst[(size_t)o * k_total + k_off + tap * cpad + c] = __float2bfloat16_rn(v);
   }
 }
 static void pack_slice(const float* src, bf16* dst, int Cout, int cseg, int c0, int cin_total, int taps, int cpad,
-                       int k_off, int k_total, cudaStream_t s) {
+                       int k_off, int k_total, cudaStream_t s, const TapOrder& order = TAPS_NATURAL) {
   const long long total = (long long)Cout * taps * cpad;
   const long long blocks = std::min<long long>((total + 255) / 256, 8192);
-  pack_slice_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, Cout, cseg, c0, cin_total, taps, cpad, k_off, k_total);
+  pack_slice_kernel<<<(int)blocks, 256, 0, s>>>(src, dst, Cout, cseg, c0, cin_total, taps, cpad, k_off, k_total, order);
   CUDA_CHECK(cudaGetLastError());
+}
+
+void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s) {
+  pack_slice(w, dst, Cout, Cin, 0, Cin, 9, Cin, 0, 9 * Cin, s, TAPS_BY_INPUT_PARITY);
 }
 
 // Identity block appended along K: out += 1.0 * x, i.e. the ResnetBlock's identity shortcut
@@ -302,6 +310,15 @@ void Engine::finalize_weights(cudaStream_t s) {
       case LayerKind::Down: {
         PackedConv* pc = pack(l.name + ".conv", l.name + ".conv", l.cout, l.c_x, 9, "", 0, 0);
         pc->bias = T_(l.name + ".conv.bias");
+        if (l.c_x % CONV_BLOCK_K == 0) {
+          // the same weights with the taps ordered by input parity: the halo kernel's stride-2 path (conv_halo.cu)
+          PackedConv s2 = *pc;
+          s2.down_perm = true;
+          s2.w = (bf16*)dalloc((size_t)l.cout * s2.k_total * sizeof(bf16));
+          pack_slice(T_(l.name + ".conv.weight"), s2.w, l.cout, l.c_x, 0, l.c_x, 9, l.c_x, 0, s2.k_total, s,
+                     TAPS_BY_INPUT_PARITY);
+          convs_[l.name + ".conv.s2"] = s2;
+        }
         break;
       }
       case LayerKind::Up: {
@@ -549,16 +566,16 @@ void Engine::build_workspace(Workspace& ws) {
   // halo-resident conv (conv_halo.cuh): 3x3 main source(s) with the GroupNorm+Swish applied in shared
   // memory, raw 1x1 shortcut sources, GroupNorm statistics of the output from the epilogue
   auto conv_halo = [&](const std::string& name, const std::vector<HaloSource>& srcs, bool up, const PackedConv& w,
-                       const float* bias, int bias_stride, const GnRef& gn, int gn_C, bool want_stats) {
+                       const float* bias, int bias_stride, const GnRef& gn, int gn_C, bool want_stats, int stride = 1) {
     const Act& a0 = srcs[0].act;
     Act probe;
-    probe.B = B; probe.H = up ? 2 * a0.H : a0.H; probe.W = up ? 2 * a0.W : a0.W; probe.C = w.cout;
+    probe.B = B; probe.H = up ? 2 * a0.H : a0.H / stride; probe.W = up ? 2 * a0.W : a0.W / stride; probe.C = w.cout;
     Act y = act(probe.H, probe.W, w.cout, want_stats ? conv_halo_stat_slots(probe, up) : 1);
     ConvStats st;
     st.partial = y.stats;
     st.slots = y.stat_slots;
     ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, true,
-                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get()));
+                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get(), stride));
     ws.n_conv++;
     return y;
   };
@@ -581,6 +598,8 @@ void Engine::build_workspace(Workspace& ws) {
           }});
           cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, no_gn, 0, true);
           ws.ops.back().flops = 2.0 * B * R * R * (double)l.cout * 9.0 * l.c_x;      // reference graph: K = 9 * in_channel
+          // HBM-bound: algorithmic bytes of the whole head = the fp32 NCHW inputs in, the bf16 NHWC activation out
+          ws.ops.back().bytes = (double)B * R * R * ((double)l.c_x * 4.0 + (double)l.cout * 2.0);
           feats.push_back(cur);
           break;
         }
@@ -600,7 +619,15 @@ void Engine::build_workspace(Workspace& ws) {
       }
       case LayerKind::Down: {
         const PackedConv& pc = convs_.at(l.name + ".conv");
-        cur = conv(l.name, cur, 9, 2, false, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H / 2, cur.W / 2, true);
+        static const bool down_umma = [] { const char* e = getenv("B200SR3_DOWN_UMMA"); return e && e[0] == '1'; }();
+        if (use_halo_ && !down_umma && convs_.count(l.name + ".conv.s2") &&
+            conv_halo_eligible(cur.H / 2, cur.W / 2, cur.C % 64 == 0, pc.cout)) {
+          // Downsample (unet.py:68-74) on the halo kernel: four input-parity views, 4 + 2 + 2 + 1 taps
+          const PackedConv& s2 = convs_.at(l.name + ".conv.s2");
+          cur = conv_halo(l.name, {HaloSource{cur, 9, -1}}, false, s2, s2.bias, 0, no_gn, 0, true, 2);
+        } else {
+          cur = conv(l.name, cur, 9, 2, false, pc, nullptr, nullptr, pc.bias, 0, nullptr, cur.H / 2, cur.W / 2, true);
+        }
         feats.push_back(cur);
         break;
       }
@@ -676,6 +703,8 @@ void Engine::build_workspace(Workspace& ws) {
           ws.ops.push_back(make_conv_halo_op(l.name + ".tail", {HaloSource{cur, 9, 0}}, false, tail_pc_,
                                              T_(l.name + ".block.3.bias"), 0, ctl_, o16, g.tab, cur.C, true, nullptr, &tl,
                                              &ws.tail_halo, g.plan.get()));
+          // HBM-bound: the bf16 activation in, the fp32 state read and written (Philox noise costs no bytes)
+          ws.ops.back().bytes = (double)B * R * R * ((double)cur.C * 2.0 + (double)oc * 8.0);
           ws.n_conv++;
           break;
         }
@@ -727,8 +756,8 @@ void Engine::ensure_graph(Workspace& ws) {
   CUDA_CHECK(e);
 }
 
-int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, double* bytes, char* names,
-                         int names_len, cudaStream_t s) {
+int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, double* flops_executed, double* bytes,
+                         char* names, int names_len, cudaStream_t s) {
   CUDA_CHECK(cudaSetDevice(device_));
   REQUIRE(T_sched_ > 0, "profile_step: no noise schedule installed");
   Workspace& ws = workspace(B, R);
@@ -752,6 +781,7 @@ int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, do
   for (int i = 0; i < n; ++i) {
     CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     if (flops) flops[i] = ws.ops[i].flops;
+    if (flops_executed) flops_executed[i] = ws.ops[i].flops_executed;
     if (bytes) bytes[i] = ws.ops[i].bytes;
     all += ws.ops[i].name;
     all += '\n';

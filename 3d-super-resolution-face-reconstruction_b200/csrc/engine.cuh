@@ -43,6 +43,8 @@ struct PackedConv {     // weights of one tensor-core conv
   bool res_identity = false;    // the 1x1 segment is an identity matrix (ResnetBlock with dim == dim_out, unet.py:101):
                                 // executed by the GEMM, but NOT a conv of the reference graph - no algorithmic FLOPs
   bool up_folded = false;       // [4*Cout][4*Cin]: parity 2x2 convs of Upsample(nearest 2x)+conv3x3
+  bool down_perm = false;       // taps ordered by input parity for the halo kernel's stride-2 path (conv_halo.cu):
+                                // (0,0) (0,2) (2,0) (2,2) | (1,0) (1,2) | (0,1) (2,1) | (1,1)
   float* bias = nullptr;        // static bias [Cout] (null when the bias comes from the table)
 };
 
@@ -52,8 +54,8 @@ struct Op {
   bool is_conv = false;
   std::function<void(cudaStream_t)> run;
   double flops = 0.0;   // algorithmic FLOPs (2*MAC on the reference graph) of one launch
-  double flops_executed = 0.0;   // what the tensor pipe runs: + identity-shortcut segments and K padding, - upsample folding
   double bytes = 0.0;   // algorithmic HBM bytes of one launch (HBM-bound kernels)
+  double flops_executed = 0.0;   // what the tensor pipe runs: + identity-shortcut segments and K padding, - upsample folding
 };
 
 class Engine;
@@ -105,8 +107,8 @@ class Engine {
   void philox_normal(uint64_t seed, int t, int64_t row_offset, int B, int R, float* out, cudaStream_t s);
   int num_snapshots() const;
   // One eager step with a CUDA event between consecutive launches: per-op device time.
-  int profile_step(int B, int R, int max_ops, float* ms, double* flops, double* bytes, char* names,
-                   int names_len, cudaStream_t s);
+  int profile_step(int B, int R, int max_ops, float* ms, double* flops, double* flops_executed, double* bytes,
+                   char* names, int names_len, cudaStream_t s);
   void layer_output(const std::string& layer, float* dst, int* C, int* H, int* W, cudaStream_t s);
 
   int64_t last_total = 0, last_conv = 0;
@@ -196,7 +198,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats,
                      const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr,
-                     const GnPlan* gn_from_stats = nullptr);   // non-null: the kernel builds the table itself (gn ignored)
+                     const GnPlan* gn_from_stats = nullptr,    // non-null: the kernel builds the table itself (gn ignored)
+                     int stride = 1);                          // 2: Downsample (unet.py:68-74), weights with down_perm
 void conv_halo_init_device();
+// OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][9*Cin] with the taps in PackedConv::down_perm order (engine.cu)
+void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s);
 
 }  // namespace b200sr3

@@ -141,10 +141,12 @@ B200SR3_API int b200sr3_last_launch_count(b200sr3_handle* h, int64_t* total, int
 
 /* Measurement aid for bench.py's roofline: runs ONE sampling step of a (B,R) batch eagerly with
  * a CUDA event between consecutive launches and reports, per launch in chain order, the device
- * time (ms), the algorithmic FLOPs (convs) and algorithmic HBM bytes (norm kernels), and the
- * newline-separated op names. Not used on the sampling path. */
+ * time (ms), the algorithmic FLOPs (convs: 2*MAC on the REFERENCE graph, SURVEY.md 8d - full-resolution Upsample
+ * convs, no identity-shortcut segments), the FLOPs the tensor pipe actually executes (optional), the algorithmic HBM
+ * bytes (HBM-bound kernels), and the newline-separated op names. Not used on the sampling path. */
 B200SR3_API int b200sr3_profile_step(b200sr3_handle* h, int B, int R, int max_ops, float* ms, double* flops,
-                                     double* bytes, char* names, int names_len, int* n_ops, void* stream);
+                                     double* flops_executed, double* bytes, char* names, int names_len, int* n_ops,
+                                     void* stream);
 
 /* Kernel-level entry used by the conv parity tests and by bench.py's roofline probe: one
  * implicit-GEMM convolution on the tcgen05 path. x: fp32 NCHW [B,Cin,H,W]; w: fp32 OIHW
@@ -163,13 +165,14 @@ B200SR3_API int b200sr3_conv2d(int device, const float* x, const float* w, const
  * (unet.py:103-110) folded in as extra K segments, and the channel concat of unet.py:261 read as
  * two sources. x0/x1/r0/r1: fp32 NCHW [B,C*,H,W] (x1, r0, r1 optional: pass NULL and 0 channels);
  * gamma/beta: [C0+C1] or NULL for no GroupNorm; w: OIHW [Cout,C0+C1,3,3]; wres: [Cout,Cr0+Cr1,1,1];
- * upsample2x applies nearest 2x to the (un-normalised) input first (unet.py:58-65, no GN, no
- * shortcut). stats_out (optional): [B][Cout][2] per-(image, channel) sum and sum of squares of y as
+ * resample = 1 applies nearest 2x to the (un-normalised) input first (Upsample, unet.py:58-65; no GN, no
+ * shortcut); resample = 2 runs the conv with stride 2 (Downsample, unet.py:68-74; one raw source, y is
+ * [B,Cout,H/2,W/2] and the shape rule applies to H/2, W/2); 0 = neither. stats_out (optional): [B][Cout][2] per-(image, channel) sum and sum of squares of y as
  * the fused GroupNorm statistics report them. H % 16 == 0, W % 8 == 0, W >= 16, channels % 64 == 0. */
 B200SR3_API int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int C1,
                    const float* gamma, const float* beta, int groups, int swish, const float* w,
                    const float* bias, const float* r0, int Cr0, const float* r1, int Cr1,
-                   const float* wres, int B, int H, int W, int Cout, int upsample2x, float* y,
+                   const float* wres, int B, int H, int W, int Cout, int resample, float* y,
                    float* stats_out, int iters, float* avg_ms, void* stream);
 
 /* ---- SR -> MICA hand-off on the device. Stand-alone entry points (no handle): all pointers are

@@ -90,7 +90,7 @@ def _gn(sd, key, x, groups):
 def noise_embedding(sd, noise_level, inner):
     """unet.py:18-31 + 179-184: [B,1] noise level -> [B,1,inner]."""
     count = inner // 2
-    step = torch.arange(count, dtype=noise_level.dtype) / count
+    step = torch.arange(count, dtype=noise_level.dtype, device=noise_level.device) / count
     enc = noise_level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     enc = torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
     h = F.linear(enc, sd[PREFIX + "noise_level_mlp.1.weight"], sd[PREFIX + "noise_level_mlp.1.bias"])
@@ -164,7 +164,7 @@ def p_sample(sd, model_opt, tabs, x, t, cond, noise, clip_denoised=True):
     """One reverse step, diffusion.py:164-187. `noise` is z_t (ignored at t == 0); cond None = the unconditional
     branch (diffusion.py:172-173: the UNet sees x alone)."""
     b = x.shape[0]
-    nl = torch.FloatTensor([tabs["sqrt_ac_prev"][t + 1]]).repeat(b, 1)
+    nl = torch.FloatTensor([tabs["sqrt_ac_prev"][t + 1]]).repeat(b, 1).to(x.device)
     eps = unet_forward(sd, model_opt, torch.cat([cond, x], dim=1) if cond is not None else x, nl)
     x0 = tabs["sqrt_recip_ac"][t] * x - tabs["sqrt_recipm1_ac"][t] * eps
     if clip_denoised:

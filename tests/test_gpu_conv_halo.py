@@ -37,6 +37,13 @@ CASES = [
     (5, 128, 64, 0, 0, 4, 4, 128, 1, 0),
     (4, 128, 0, 0, 0, 4, 4, 128, 0, 1),             # folded upsample 4 -> 8
     (11, 64, 0, 64, 0, 4, 4, 64, 1, 0),             # three tiles, the last one holds a single image
+    # stride-2 Downsample (unet.py:68-74): `up` = 2, H x W is the INPUT size; four input-parity views, 4 + 2 + 2 + 1 taps
+    (2, 64, 0, 0, 0, 128, 128, 64, 0, 2),           # downs.3 of the headline: 128 -> 64
+    (3, 128, 0, 0, 0, 32, 32, 128, 0, 2),           # 32 -> 16: one 8x16 tile row pair per image
+    (1, 256, 0, 0, 0, 64, 32, 256, 0, 2),           # non-square
+    (5, 512, 0, 0, 0, 16, 16, 512, 0, 2),           # 16 -> 8: two output images per tile, odd batch
+    (7, 512, 0, 0, 0, 8, 8, 512, 0, 2),             # 8 -> 4: five output images per tile
+    (1, 64, 0, 0, 0, 32, 32, 128, 0, 2),            # Cin != Cout
 ]
 SHAPES = [(0, 0), (64, 1), (64, 2), (128, 1), (128, 2), (256, 1)]
 
@@ -46,8 +53,7 @@ def _block(x0, x1, gamma, beta, w, b, r0, r1, wres, up, want_stats=True, iters=0
     lib = _lib.load()
     B, C0, H, W = x0.shape
     Cout = w.shape[0]
-    s = 2 if up else 1
-    y = torch.empty(B, Cout, H * s, W * s, device="cuda")
+    y = torch.empty((B, Cout, H // 2, W // 2) if up == 2 else (B, Cout, H * (1 + up), W * (1 + up)), device="cuda")
     st = torch.empty(B, Cout, 2, device="cuda") if want_stats else None
     P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
     ch = lambda t: t.shape[1] if t is not None else 0
@@ -64,9 +70,9 @@ def _reference(x0, x1, gamma, beta, w, b, r0, r1, wres, up):
     if gamma is not None:
         xin = F.group_norm(xin, 32, gamma, beta, eps=1e-5)
         xin = r(xin * torch.sigmoid(xin))
-    if up:
+    if up == 1:
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
-    y = F.conv2d(xin.double(), r(w).double(), b.double(), padding=1)
+    y = F.conv2d(xin.double(), r(w).double(), b.double(), padding=1, stride=2 if up == 2 else 1)
     if r0 is not None:
         rin = r(r0) if r1 is None else torch.cat([r(r0), r(r1)], 1)
         y = y + F.conv2d(rin.double(), r(wres).double())
@@ -104,7 +110,7 @@ def test_block_matches_torch(case):
     err = (st.cpu() - s_ref).abs()
     # (a folded upsample pre-sums the 3x3 weights in fp32 and rounds once, the reference rounds each
     # weight: a per-channel systematic difference that grows with n, not sqrt(n))
-    assert float(err[..., 0].max()) <= 4e-3 * rms * n ** 0.5 * 4 + 1e-2 + (3e-3 * rms * n if case[9] else 0)
+    assert float(err[..., 0].max()) <= 4e-3 * rms * n ** 0.5 * 4 + 1e-2 + (3e-3 * rms * n if case[9] == 1 else 0)
     # sum of squares of the bf16-ROUNDED output: each y carries <= 2^-9 relative rounding error, i.e. 2^-8 on y^2 (this
     # term does not average out over the 16 pixels of a 4x4 image), plus the accumulation noise bound used above
     assert bool((err[..., 1] <= 2 ** -7 * s_ref[..., 1] + 1e-2 * rms * rms * n).all())

@@ -25,14 +25,14 @@ def main():
     net.set_new_noise_schedule(opt["sr"]["model"]["beta_schedule"]["val"], [torch.device("cuda")])
     net.profile_step(B, R)
     prof = net.profile_step(B, R)
-    total = sum(ms for _, ms, _, _ in prof)
+    total = sum(p[1] for p in prof)
     rows = []
-    for name, ms, fl, by in prof:
+    for name, ms, fl, by, fx in prof:
         rate = f"{fl / ms / 1e9:8.1f} TF/s" if fl > 0 else (f"{by / ms / 1e6:8.1f} GB/s" if by > 0 else " " * 13)
-        rows.append({"op": name, "ms": ms, "flops": fl, "bytes": by})
+        rows.append({"op": name, "ms": ms, "flops": fl, "bytes": by, "flops_executed": fx})
         print(f"{name:28s} {ms * 1e3:9.1f} us {100 * ms / total:5.1f}%  {rate}")
     kinds = {}
-    for name, ms, fl, by in prof:
+    for name, ms, fl, by, fx in prof:
         k = "conv" if fl > 0 else name.split(".")[-1]
         kinds[k] = kinds.get(k, 0.0) + ms
     print("---- total %.3f ms" % total)
