@@ -33,6 +33,10 @@ void conv_halo_init_device() {
   set_attr<64, 1, false, 0, 2>();  set_attr<64, 1, true, 0, 2>();
   set_attr<128, 1, false, 0, 2>(); set_attr<128, 1, true, 0, 2>();
   set_attr<256, 1, false, 0, 2>(); set_attr<256, 1, true, 0, 2>();
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<64, 1, 0, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<64, 2, 0, 1>::TOTAL));
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -105,7 +109,8 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
-                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats, int stride) {
+                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats, int stride,
+                     const HaloHead* head) {
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
   REQUIRE(stride == 1 || stride == 2, "halo conv: stride 1 or 2");
@@ -115,6 +120,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                           a0.H % 2 == 0 && a0.W % 2 == 0 && w.down_perm),
           "halo conv: a stride-2 conv is one raw 3x3 source with parity-ordered weights");
   REQUIRE(stride == 2 || !w.down_perm, "halo conv: parity-ordered weights belong to a stride-2 conv");
+  // head: the single source is virtual (64 split-precision channels built in shared memory from the fp32 inputs)
+  REQUIRE(!head || (srcs.size() == 1 && srcs[0].ntaps == 9 && srcs[0].gn_off < 0 && srcs[0].act.C == CONV_BLOCK_K &&
+                    stride == 1 && !upsample2x && !tail && head->x && head->cc >= 0 && head->cx >= 1 &&
+                    (head->cc + head->cx <= 4 || head->cc + head->cx == 6 || head->cc + head->cx == 8) &&
+                    (head->cc == 0 || head->cond)),
+          "halo conv: the head is one raw 3x3 over <= 8 fp32 input channels");
   const int PH = a0.H / stride, PW = a0.W / stride;
   auto pp = std::make_shared<ConvHaloParams>();
   ConvHaloParams& p = *pp;
@@ -190,7 +201,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     REQUIRE(a.B == out.B && a.H == PH && a.W == PW && a.C % CONV_BLOCK_K == 0, "halo conv: source shape mismatch");
     REQUIRE(s.ntaps == 9 || s.ntaps == 1, "halo conv: a source is 3x3 or 1x1");
     REQUIRE(!(upsample2x && s.ntaps == 1), "halo conv: a folded upsample has no shortcut");
-    encode_src((int)i, a.ptr, a.C, a.W, a.H, (size_t)a.C, (size_t)a.W * a.C, (size_t)a.H * a.W * a.C);
+    if (!head) encode_src((int)i, a.ptr, a.C, a.W, a.H, (size_t)a.C, (size_t)a.W * a.C, (size_t)a.H * a.W * a.C);
     HaloSeg& sg = p.seg[i];
     sg.map = (int)i;
     sg.cblocks = a.C / CONV_BLOCK_K;
@@ -246,6 +257,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   if (tail) {
     p.tail_x = tail->x; p.tail_eps = tail->eps_out; p.coefs = tail->coefs; p.tail_oc = tail->oc;
   }
+  if (head) {
+    p.head_cond = head->cond; p.head_x = head->x; p.head_cc = head->cc; p.head_cx = head->cx;
+  }
+  const bool is_head = head != nullptr;
   for (int par = 0; par < p.num_par && !tail; ++par) {
     const int sc = upsample2x ? 2 : 1;
     const int py = par >> 1, px = par & 1;
@@ -294,6 +309,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       if ((c[2] == 2) != (pass == 0)) continue;
       if (c[2] == 2 && c[0] < cg_min_bn) continue;
       if ((c[0] == 16) != (tail != nullptr)) continue;
+      if (is_head && c[0] != 64) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (g2 && c[0] != 64) continue;
       if (c[0] == 128 && c[1] == 2 && !allow_128x2) continue;
@@ -358,8 +374,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
     op.flops_executed = 2.0 * m * (double)out.C * k_exec;
   }
-  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2](cudaStream_t s) {
-    if (cg == 2) {
+  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head](cudaStream_t s) {
+    if (is_head) {
+      if (mt == 2) launch_pdl(conv_halo_kernel<64, 2, false, 0, 1, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 2, 0, 1>::TOTAL, s, *pp);
+      else launch_pdl(conv_halo_kernel<64, 1, false, 0, 1, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 0, 1>::TOTAL, s, *pp);
+    } else if (cg == 2) {
       if (bn == 256) launch_halo_pair<256>(*pp, any_gn, grid, s);
       else if (bn == 128) launch_halo_pair<128>(*pp, any_gn, grid, s);
       else launch_halo_pair<64>(*pp, any_gn, grid, s);

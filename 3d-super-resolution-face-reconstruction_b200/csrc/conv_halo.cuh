@@ -257,6 +257,21 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Split-precision operand row of the head conv: N fp32 inputs -> hi | lo | hi (bf16-exact floats), zero padded to 32
+// (launch_pack_head_split_weight carries w_hi | w_hi | w_lo in the same positions).
+template <int N>
+__device__ __forceinline__ void halo_head_row(const float* v, float* row) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) row[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    const float hi = __bfloat162float(__float2bfloat16_rn(v[c]));
+    row[c] = hi;
+    row[N + c] = v[c] - hi;
+    row[2 * N + c] = hi;
+  }
+}
+
 // Role timing is a COMPILE-TIME option (-DB200SR3_ROLE_TIMING=1, `build.py --timing` -> libb200sr3_timing.so): with the
 // counters compiled in, every hot loop carries parameter loads, clock reads and branches, and the kernel's hot code set
 // grows - measured, unrolling the nine taps of the issue loop alone (more code, fewer instructions executed) cost 6 %.
@@ -515,7 +530,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   if (warp == LW) {
     halo0_issued = CG == 1 && !p.pdl && sup_begin < sup_end;      // uniform over the warp
     if (lane == 0) {
-      ptx::prefetch_tmap(&p.a_map[p.seg[0].map]);
+      if (!HEAD) ptx::prefetch_tmap(&p.a_map[p.seg[0].map]);
       for (int s = 0; s < AST; ++s) {
         ptx::mbar_init(a_full(s), 1);
         ptx::mbar_init(a_ready(s), CG == 2 ? 16 : 256);      // pair: one arrival per transform warp of both CTAs
@@ -530,7 +545,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         for (int m = 0; m < MT; ++m) { t[m] = w0; tile_next(w0); }
         issue_halo(0, p.seg[0].map, 0, t);
       }
-      for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
+      if (!HEAD) for (int i = 0; i < p.num_segs; ++i) ptx::prefetch_tmap(&p.a_map[i]);
     }
     __syncwarp();
   }
@@ -1107,20 +1122,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
                 float row[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) row[i] = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  // slots c, n + c, 2n + c with run-time n: selects over the unrolled row (no local-memory indexing)
-                  const float hi = __bfloat162float(__float2bfloat16_rn(v[m][c]));
-                  const float lo = v[m][c] - hi;
-#pragma unroll
-                  for (int i = 0; i < 24; ++i) {
-                    if (c < n && i == c) row[i] = hi;
-                    if (c < n && i == n + c) row[i] = lo;
-                    if (c < n && i == 2 * n + c) row[i] = hi;
-                  }
-                }
+                if (n == 6) halo_head_row<6>(v[m], row);      // (compile-time channel counts: constant register indices)
+                else if (n == 2) halo_head_row<2>(v[m], row);
+                else if (n == 8) halo_head_row<8>(v[m], row);
+                else if (n == 3) halo_head_row<3>(v[m], row);
+                else if (n == 4) halo_head_row<4>(v[m], row);
+                else halo_head_row<1>(v[m], row);
                 uint8_t* dst = smem_gen + as * S::A_STAGE + m * G::STRIDE + tt * 128;
 #pragma unroll
                 for (int jj = 0; jj < 2 * KSTEPS; ++jj)

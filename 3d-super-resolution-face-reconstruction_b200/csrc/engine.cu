@@ -300,7 +300,7 @@ void Engine::finalize_weights(cudaStream_t s) {
         head_w_ = (float*)dalloc((size_t)l.cout * l.c_x * 9 * sizeof(float));
         launch_pack_head_weight(T_(l.name + ".weight"), head_w_, l.cout, l.c_x, s);
         head_pc_ = PackedConv();
-        if ((l.c_x == 2 || l.c_x == 6 || l.c_x == 8) && l.cout % 64 == 0) {
+        if ((l.c_x == 1 || l.c_x == 2 || l.c_x == 3 || l.c_x == 4 || l.c_x == 6 || l.c_x == 8) && l.cout % 64 == 0) {
           head_pc_.cout = l.cout; head_pc_.taps = 9; head_pc_.cin_main = CONV_BLOCK_K; head_pc_.k_total = 9 * CONV_BLOCK_K;
           head_pc_.w = (bf16*)dalloc((size_t)l.cout * head_pc_.k_total * sizeof(bf16));
           launch_pack_head_split_weight(T_(l.name + ".weight"), head_pc_.w, l.cout, l.c_x, s);
@@ -587,16 +587,33 @@ void Engine::build_workspace(Workspace& ws) {
     switch (l.kind) {
       case LayerKind::HeadConv: {
         if (use_halo_ && head_pc_.w && conv_halo_eligible(R, R, 1, l.cout)) {
-          // downs.0 on the tensor cores: split-precision operand (x_t is never rounded), then a halo conv
-          Act hp = act(R, R, CONV_BLOCK_K);
+          // downs.0 on the tensor cores, straight from the fp32 NCHW sampler state: the kernel's transform warps build
+          // the split-precision operand (x_t is never rounded to bf16) in shared memory - nothing is packed in HBM.
+          // (B200SR3_HEAD_PACK=1: the earlier two-launch form, pack kernel + plain halo conv, for A/B.)
           const float* cond = cfg_.conditional ? ws.cond : nullptr;
           const int cc = cfg_.conditional ? oc : 0;
-          const float* xw = ws.x;
-          bf16* hdst = hp.ptr;
-          ws.ops.push_back(Op{l.name + ".pack", false, [=](cudaStream_t s) {
-            launch_head_pack(cond, xw, cc, oc, B, R, hdst, s);
-          }});
-          cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, no_gn, 0, true);
+          static const bool head_pack = [] { const char* e = getenv("B200SR3_HEAD_PACK"); return e && e[0] == '1'; }();
+          if (head_pack && (l.c_x == 2 || l.c_x == 6 || l.c_x == 8)) {
+            Act hp = act(R, R, CONV_BLOCK_K);
+            const float* xw = ws.x;
+            bf16* hdst = hp.ptr;
+            ws.ops.push_back(Op{l.name + ".pack", false, [=](cudaStream_t s) {
+              launch_head_pack(cond, xw, cc, oc, B, R, hdst, s);
+            }});
+            cur = conv_halo(l.name, {HaloSource{hp, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0, no_gn, 0, true);
+          } else {
+            Act virt;                       // the operand the kernel builds on the fly: 64 channels, never in memory
+            virt.B = B; virt.H = R; virt.W = R; virt.C = CONV_BLOCK_K;
+            HaloHead hh;
+            hh.cond = cond; hh.x = ws.x; hh.cc = cc; hh.cx = oc;
+            cur = act(R, R, l.cout, conv_halo_stat_slots(Act{nullptr, nullptr, 1, B, R, R, l.cout}, false));
+            ConvStats st;
+            st.partial = cur.stats;
+            st.slots = cur.stat_slots;
+            ws.ops.push_back(make_conv_halo_op(l.name, {HaloSource{virt, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0,
+                                               ctl_, cur, nullptr, 0, true, &st, nullptr, nullptr, nullptr, 1, &hh));
+            ws.n_conv++;
+          }
           ws.ops.back().flops = 2.0 * B * R * R * (double)l.cout * 9.0 * l.c_x;      // reference graph: K = 9 * in_channel
           // HBM-bound: algorithmic bytes of the whole head = the fp32 NCHW inputs in, the bf16 NHWC activation out
           ws.ops.back().bytes = (double)B * R * R * ((double)l.c_x * 4.0 + (double)l.cout * 2.0);

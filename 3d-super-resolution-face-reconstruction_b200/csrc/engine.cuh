@@ -188,6 +188,11 @@ struct HaloSource {
 };
 bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout);
 int conv_halo_stat_slots(const Act& out, bool upsample2x);
+struct HaloHead {      // downs.0 (unet.py:187) reading cat([cond, x], 1) (diffusion.py:170) as fp32 NCHW, no packed operand
+  const float* cond = nullptr;   // [B][cc][R][R] or null
+  const float* x = nullptr;      // [B][cx][R][R]
+  int cc = 0, cx = 0;
+};
 struct HaloTail {      // final_conv fused with the sampler update (conv_halo.cuh, BLOCK_N == 16)
   float* x = nullptr;          // fp32 NCHW state, updated in place (null: eps only)
   float* eps_out = nullptr;    // optional fp32 NCHW eps
@@ -199,7 +204,8 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats,
                      const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr,
                      const GnPlan* gn_from_stats = nullptr,    // non-null: the kernel builds the table itself (gn ignored)
-                     int stride = 1);                          // 2: Downsample (unet.py:68-74), weights with down_perm
+                     int stride = 1,                           // 2: Downsample (unet.py:68-74), weights with down_perm
+                     const struct HaloHead* head = nullptr);   // non-null: downs.0 straight from the fp32 NCHW inputs
 void conv_halo_init_device();
 // OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][9*Cin] with the taps in PackedConv::down_perm order (engine.cu)
 void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s);
