@@ -33,6 +33,10 @@ void conv_halo_init_device() {
   set_attr<64, 1, false, 0, 2>();  set_attr<64, 1, true, 0, 2>();
   set_attr<128, 1, false, 0, 2>(); set_attr<128, 1, true, 0, 2>();
   set_attr<256, 1, false, 0, 2>(); set_attr<256, 1, true, 0, 2>();
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<64, 1, 0, 1, true>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HaloSmem<128, 1, 0, 1, true>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, false, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HaloSmem<64, 1, 0, 1>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 2, false, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -334,6 +338,21 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     }
     REQUIRE(bn != 0, "halo conv: no tile shape fits (check B200SR3_HALO_BN / B200SR3_HALO_MT)");
   }
+  // Deep halo ring (conv_halo.cuh, DEEP): conv2 layers whose K loop is mostly single-tap shortcut stages. Rules from the
+  // same-box A/B in profiles/r02d_ab.txt; B200SR3_HALO_DEEP=0 switches it off, =1 forces it wherever it is instantiated.
+  bool deep = false;
+  {
+    int sc_blocks = 0, main_blocks = 0;
+    for (int i = 0; i < p.num_segs; ++i) (p.seg[i].ntaps == 1 ? sc_blocks : main_blocks) += p.seg[i].cblocks;
+    const char* e = getenv("B200SR3_HALO_DEEP");
+    const int force = e ? atoi(e) : -1;
+    const bool can = !g1 && cg == 1 && !tail && !is_head && any_gn && stride == 1 && !upsample2x && (bn == 64 || bn == 128) &&
+                     !getenv("B200SR3_HALO_BN") && !getenv("B200SR3_HALO_MT");
+    if (can && force != 0) {
+      if (bn == 64 && (sc_blocks >= 2 || force == 1)) { deep = true; mt = 1; }
+      else if (bn == 128 && mt == 1 && ((sc_blocks >= 1 && main_blocks <= 2) || force == 1)) deep = true;
+    }
+  }
   p.tiles_n = out.C / bn;
   p.total_super = (int)(m_tiles / (mt * cg) * p.tiles_n);
   p.seg_len_super = (int)(tiles_img * p.num_par / (mt * cg));
@@ -374,8 +393,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
     op.flops_executed = 2.0 * m * (double)out.C * k_exec;
   }
-  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head](cudaStream_t s) {
-    if (is_head) {
+  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head, deep](cudaStream_t s) {
+    if (deep) {
+      if (bn == 64) launch_pdl(conv_halo_kernel<64, 1, true, 0, 1, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 0, 1, true>::TOTAL, s, *pp);
+      else launch_pdl(conv_halo_kernel<128, 1, true, 0, 1, false, true>, dim3(grid), dim3(halo_threads(128)), HaloSmem<128, 1, 0, 1, true>::TOTAL, s, *pp);
+    } else if (is_head) {
       if (mt == 2) launch_pdl(conv_halo_kernel<64, 2, false, 0, 1, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 2, 0, 1>::TOTAL, s, *pp);
       else launch_pdl(conv_halo_kernel<64, 1, false, 0, 1, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 0, 1>::TOTAL, s, *pp);
     } else if (cg == 2) {

@@ -51,7 +51,17 @@ constexpr int halo_esets(int block_n) { return (void)block_n, 1; }
 constexpr int halo_threads(int block_n) { return 512 + 128 * (halo_esets(block_n) - 1); }
 // halo ring depth: 3 (load / transform / MMA). A 6-deep ring for one-tile BLOCK_N = 64 shapes was tried for
 // the single-tap shortcut segments and does not pay: those layers are shared-memory-bandwidth bound.
-constexpr int halo_a_stages(int block_n, int mt, int geo) { return (void)block_n, (void)mt, (void)geo, 3; }
+// DEEP ring (template flag, one-tile GEO 0 shapes with BLOCK_N <= 128): conv2 of a ResnetBlock whose shortcut is a res_conv
+// over a concatenated input (unet.py:103-110,261) walks 1 + (2..6) halo stages per tile, all but the first single-tap. With
+// three stages the NEXT tile's main stage cannot be fetched and transformed while this tile's MMAs run (role counters,
+// profiles/r02c_roles.txt: the MMA issuer waited 4.2 k of 11.1 k cycles per super tile on `64->64 + res192 @128`; ncu:
+// shared-memory pipe 50 %, TMA 17 %, DRAM 44 % - a latency-bound pipeline, not a bandwidth-bound one). Measured on B200
+// (profiles/r02d_ab.txt, burst): 99.1 -> 89.5 us (64 + res192), 89.3 -> 81.2 (64 + res128), 65.5 -> 61.7 / 54.0 -> 49.2 /
+// 49.4 -> 46.3 (128-channel conv2 layers); layers of 9-tap blocks only lose 4-13 % (fewer weight stages fit), so the host
+// picks it per layer.
+constexpr int halo_a_stages(int block_n, int mt, int geo, bool deep = false) {
+  return (deep && geo == 0 && mt == 1) ? (block_n == 64 ? 6 : (block_n == 128 ? 5 : 3)) : 3;
+}
 constexpr int HALO_MAX_SEGS = 4;
 
 // Tile geometry. GEO 0: an 8 x 16 pixel tile of one image, halo 10 x 18. GEO 1 (8 x 8 images): a tile is
@@ -150,10 +160,10 @@ struct alignas(64) ConvHaloParams {
 };
 
 #ifdef __CUDACC__
-template <int BLOCK_N, int MT, int GEO = 0, int CG = 1>
+template <int BLOCK_N, int MT, int GEO = 0, int CG = 1, bool DEEP = false>
 struct HaloSmem {
   static constexpr int A_STAGE = MT * HaloGeo<GEO>::STRIDE;
-  static constexpr int AST = halo_a_stages(BLOCK_N, MT, GEO);
+  static constexpr int AST = halo_a_stages(BLOCK_N, MT, GEO, DEEP);
   static constexpr int A_BYTES = AST * A_STAGE;
   static constexpr int W_STAGE = (BLOCK_N / CG) * 128;           // a CTA of a cta_group::2 pair holds half the weight tile
   static constexpr int NSTG = (BLOCK_N == 256 || MT == 2) ? 1 : 2;   // staging slabs per epilogue warp
@@ -406,10 +416,11 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
 // per MMA from (4 + N/32) KB to (4 + N/64) KB. The leader (rank 0) issues the MMAs; its barriers collect both CTAs'
 // weight loads (TMA in cta_group::2 form signals the leader's barrier), transform arrivals and epilogue releases;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
-template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = false>
+template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = false, bool DEEP = false>
 __global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
-  using S = HaloSmem<BLOCK_N, MT, GEO, CG>;
+  using S = HaloSmem<BLOCK_N, MT, GEO, CG, DEEP>;
+  static_assert(!DEEP || (GEO == 0 && MT == 1 && CG == 1 && !HEAD && (BLOCK_N == 64 || BLOCK_N == 128)), "deep ring: one-tile shapes");
   static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
   static_assert(!HEAD || (!FUSE_GN && GEO == 0 && CG == 1 && BLOCK_N == 64), "the head conv is a raw 3x3, Cout = 64");
   constexpr bool XF = FUSE_GN || CG == 2 || HEAD;      // transform warps active (in a pair they also forward "halo landed" to the leader)

@@ -18,6 +18,10 @@ SHAPES = [
     ("c1 64+64->64 @128", 64, 64, 0, 0, 128, 64, 0),
     ("c1 128+64->64 @128", 128, 64, 0, 0, 128, 64, 0),
     ("c2 64->64+res192 @128", 64, 0, 128, 64, 128, 64, 0),
+    ("c2 64->64+res128 @128", 64, 0, 64, 64, 128, 64, 0),
+    ("c2 128->128+res384 @64", 128, 0, 256, 128, 64, 128, 0),
+    ("c2 128->128+res192 @64", 128, 0, 128, 64, 64, 128, 0),
+    ("c2 256->256+res768 @32", 256, 0, 512, 256, 32, 256, 0),
     ("c1 128->128 @64", 128, 0, 0, 0, 64, 128, 0),
     ("c2 128->128+id @64", 128, 0, 128, 0, 64, 128, 0),
     ("c1 256+128->128 @64", 256, 128, 0, 0, 64, 128, 0),
