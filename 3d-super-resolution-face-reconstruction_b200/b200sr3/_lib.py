@@ -55,6 +55,16 @@ _SIGNATURES = {
     "b200sr3_tensor2img": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "b200sr3_mica_handoff": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "b200sr3_tensor_blob": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "b200sr3_mica_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "b200sr3_mica_destroy": (C.c_int, [_P]),
+    "b200sr3_mica_num_tensors": (C.c_int, [_P]),
+    "b200sr3_mica_tensor_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "b200sr3_mica_load_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "b200sr3_mica_finalize_weights": (C.c_int, [_P, _P]),
+    "b200sr3_mica_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "b200sr3_mica_layer_output": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "b200sr3_mica_profile": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_char_p,
+                                       C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

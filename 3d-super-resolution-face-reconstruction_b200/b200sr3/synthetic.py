@@ -41,3 +41,33 @@ def inputs(batch, res, n_noise=0, seed=123):
         return cond
     noise = torch.from_numpy(rng.standard_normal((n_noise, batch, 3, res, res)).astype(np.float32))
     return cond, noise
+
+
+def mica_state_dict(module, seed=0):
+    """Seeded weights for b200sr3.Arcface / MappingNetwork (or any module made of conv / linear / BatchNorm / PReLU):
+    conv and linear weights U(-b, b) with b = sqrt(3 / fan_in) (unit gain), BatchNorm with non-trivial affine
+    parameters and running statistics (the last BatchNorm of a residual branch, `bn3`, at 0.3 so that the residual
+    stream stays O(1) over 49 blocks), PReLU slopes around 0.25. The reference's own init (conv ~ N(0, 0.1),
+    arcface.py:112-118) is meant for training with batch statistics and overflows fp32 in eval mode."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for name, t in module.state_dict().items():
+        shape = tuple(t.shape)
+        leaf = name.rsplit(".", 1)[-1]
+        owner = name.rsplit(".", 2)[-2] if name.count(".") else ""
+        if leaf == "num_batches_tracked":
+            v = np.asarray(1000)
+        elif leaf == "running_mean":
+            v = 0.1 * rng.standard_normal(shape)
+        elif leaf == "running_var":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif len(shape) >= 2:
+            v = rng.uniform(-1, 1, size=shape) * math.sqrt(3.0 / int(np.prod(shape[1:])))
+        elif owner.startswith("prelu"):
+            v = 0.25 + 0.05 * rng.standard_normal(shape)
+        elif leaf == "weight":
+            v = (0.3 if owner == "bn3" else 1.0) * (1.0 + 0.1 * rng.standard_normal(shape))
+        else:
+            v = 0.1 * rng.standard_normal(shape)
+        out[name] = torch.from_numpy(np.ascontiguousarray(np.asarray(v).astype(np.int64 if leaf == "num_batches_tracked" else np.float32))).reshape(shape)
+    return out

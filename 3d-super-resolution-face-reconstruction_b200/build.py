@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200sr3", "libb200sr3.so")
-SOURCES = ["abi.cu", "engine.cu", "conv_umma.cu", "conv_halo.cu", "kernels.cu", "handoff.cu"]
-HEADERS = ["common.cuh", "conv_umma.cuh", "conv_halo.cuh", "kernels.cuh", "engine.cuh", os.path.join("..", "..", "include", "b200sr3.h")]
+SOURCES = ["abi.cu", "engine.cu", "conv_umma.cu", "conv_halo.cu", "kernels.cu", "handoff.cu", "arcface.cu"]
+HEADERS = ["common.cuh", "conv_umma.cuh", "conv_halo.cuh", "kernels.cuh", "engine.cuh", "arcface.cuh", os.path.join("..", "..", "include", "b200sr3.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

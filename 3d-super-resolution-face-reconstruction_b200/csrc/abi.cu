@@ -4,12 +4,16 @@
 #include <cstring>
 #include <string>
 
+#include "arcface.cuh"
 #include "engine.cuh"
 
 using namespace b200sr3;
 
 struct b200sr3_handle {
   Engine* engine;
+};
+struct b200sr3_mica {
+  MicaEncoder* enc;
 };
 
 static thread_local std::string g_last_error;
@@ -458,5 +462,77 @@ int b200sr3_tensor_blob(const float* x, int B, int R, float* arcface_blob, void*
   return guarded([&] { launch_tensor_blob(x, B, R, arcface_blob, (cudaStream_t)stream); });
 }
 
+
+// ---- MICA identity encoder (arcface.cu)
+static MicaEncoder& M(b200sr3_mica* h) {
+  if (!h || !h->enc) throw Error("null mica handle");
+  return *h->enc;
+}
+
+int b200sr3_mica_create(int device, int z_dim, int map_hidden_dim, int map_layers, int n_shape, b200sr3_mica** out) {
+  return guarded([&] {
+    REQUIRE(out, "mica_create: null argument");
+    *out = nullptr;
+    MicaEncoder* e = new MicaEncoder(device, z_dim, map_hidden_dim, map_layers, n_shape);
+    *out = new b200sr3_mica{e};
+  });
+}
+
+int b200sr3_mica_destroy(b200sr3_mica* h) {
+  return guarded([&] {
+    if (!h) return;
+    delete h->enc;
+    delete h;
+  });
+}
+
+int b200sr3_mica_num_tensors(b200sr3_mica* h) {
+  int n = -1;
+  guarded([&] { n = M(h).num_tensors(); });
+  return n;
+}
+
+int b200sr3_mica_tensor_info(b200sr3_mica* h, int index, const char** key, int64_t shape[4], int* ndim) {
+  return guarded([&] {
+    const TensorSpec& t = M(h).tensor(index);
+    if (key) *key = t.key.c_str();
+    if (ndim) *ndim = (int)t.shape.size();
+    if (shape)
+      for (size_t i = 0; i < 4; ++i) shape[i] = i < t.shape.size() ? t.shape[i] : 1;
+  });
+}
+
+int b200sr3_mica_load_tensor(b200sr3_mica* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  return guarded([&] {
+    REQUIRE(key && shape, "mica_load_tensor: null argument");
+    M(h).load_tensor(key, data, shape, ndim);
+  });
+}
+
+int b200sr3_mica_finalize_weights(b200sr3_mica* h, void* stream) {
+  return guarded([&] { M(h).finalize_weights((cudaStream_t)stream); });
+}
+
+int b200sr3_mica_encode(b200sr3_mica* h, const float* arcface_blob, int B, float* embedding, float* identity,
+                        float* shape_code, void* stream) {
+  return guarded([&] { M(h).encode(arcface_blob, B, embedding, identity, shape_code, (cudaStream_t)stream); });
+}
+
+int b200sr3_mica_layer_output(b200sr3_mica* h, const char* layer, float* dst, int* C, int* H, int* W, void* stream) {
+  return guarded([&] {
+    REQUIRE(layer, "mica_layer_output: null name");
+    M(h).layer_output(layer, dst, C, H, W, (cudaStream_t)stream);
+  });
+}
+
+int b200sr3_mica_profile(b200sr3_mica* h, int B, int max_ops, float* ms, double* flops, char* names, int names_len,
+                         int* n_ops, int64_t* launches, int64_t* conv_launches, void* stream) {
+  return guarded([&] {
+    REQUIRE(ms && n_ops, "mica_profile: null argument");
+    *n_ops = M(h).profile(B, max_ops, ms, flops, names, names_len, (cudaStream_t)stream);
+    if (launches) *launches = M(h).last_total;
+    if (conv_launches) *conv_launches = M(h).last_conv;
+  });
+}
 
 }  // extern "C"

@@ -33,6 +33,10 @@ void conv_halo_init_device() {
   set_attr<64, 1, false, 0, 2>();  set_attr<64, 1, true, 0, 2>();
   set_attr<128, 1, false, 0, 2>(); set_attr<128, 1, true, 0, 2>();
   set_attr<256, 1, false, 0, 2>(); set_attr<256, 1, true, 0, 2>();
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<64, 1, 0, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 2, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<64, 2, 0, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<128, 1, 0, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256, 1, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<256, 1, 0, 1>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HaloSmem<64, 1, 0, 1, true>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -114,15 +118,20 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
                      std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats, int stride,
-                     const HaloHead* head) {
+                     const HaloHead* head, const float* prelu_slope, bool partial_tiles) {
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
   REQUIRE(stride == 1 || stride == 2, "halo conv: stride 1 or 2");
   // stride 2 (Downsample, unet.py:68-74): the tiles walk the OUTPUT grid and the input is read through its four
   // (row parity, column parity) sub-grids, each a strided view with its own tensor map - see the segment list below
-  REQUIRE(stride == 1 || (srcs.size() == 1 && srcs[0].ntaps == 9 && srcs[0].gn_off < 0 && !upsample2x && !tail &&
-                          a0.H % 2 == 0 && a0.W % 2 == 0 && w.down_perm),
-          "halo conv: a stride-2 conv is one raw 3x3 source with parity-ordered weights");
+  REQUIRE(stride == 1 || (srcs[0].ntaps == 9 && !upsample2x && !tail && a0.H % 2 == 0 && a0.W % 2 == 0 && w.down_perm &&
+                          srcs.size() <= 3),
+          "halo conv: a stride-2 conv is one 3x3 source with parity-ordered weights (plus at most two 1x1 shortcut sources)");
+  const bool prelu = prelu_slope != nullptr;      // transform = per-channel affine + PReLU (ArcFace), not GroupNorm + Swish
+  REQUIRE(!prelu || (gn != nullptr && !gn_from_stats && !tail && !upsample2x && !head),
+          "halo conv: the affine + PReLU transform takes a ready (scale, shift) row");
+  REQUIRE(!partial_tiles || (!(stats && stats->partial) && !tail && !upsample2x),
+          "halo conv: partial tiles are for convs that publish no statistics");
   REQUIRE(stride == 2 || !w.down_perm, "halo conv: parity-ordered weights belong to a stride-2 conv");
   // head: the single source is virtual (64 split-precision channels built in shared memory from the fp32 inputs)
   REQUIRE(!head || (srcs.size() == 1 && srcs[0].ntaps == 9 && srcs[0].gn_off < 0 && srcs[0].act.C == CONV_BLOCK_K &&
@@ -137,10 +146,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.num_par = upsample2x ? 4 : 1;
   REQUIRE(out.B == a0.B && out.H == (upsample2x ? 2 : 1) * PH && out.W == (upsample2x ? 2 : 1) * PW,
           "halo conv: output shape mismatch");
-  const bool g2 = geo2(PH, PW);
-  const bool g1 = geo1(PH, PW) || g2;      // a multi-image geometry (one tile per unit of 2 or 3 whole images)
-  const int gi = geo_imgs(PH, PW);
-  REQUIRE(g1 || (PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16), "halo conv: unsupported spatial size");
+  // partial tiles (ArcFace: 56, 28, 14, 7 px): always the one-image geometry; tiles hanging over the right / bottom edge
+  // load zeros there (TMA fill = the conv's padding) and their stores are clipped by the output tensor map
+  const bool g2 = !partial_tiles && geo2(PH, PW);
+  const bool g1 = !partial_tiles && (geo1(PH, PW) || g2);      // a multi-image geometry (one tile per unit of 2 or 5 whole images)
+  const int gi = partial_tiles ? 1 : geo_imgs(PH, PW);
+  REQUIRE(g1 || partial_tiles || (PH % HALO_TH == 0 && PW % HALO_TW == 0 && PW >= 16), "halo conv: unsupported spatial size");
   REQUIRE(!(g1 && tail), "halo conv: the tail runs on the one-image geometry");
   if (tail) {
     REQUIRE(out.C == 16 && w.cout == 16 && tail->oc >= 1 && tail->oc <= 4 && !upsample2x && !(stats && stats->partial),
@@ -174,7 +185,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                               estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(halo) failed with CUresult " + std::to_string((int)r));
   };
-  const int pitch = g2 ? 5 : (geo1(PH, PW) ? 20 : HALO_W);      // pixels per halo-tile row (HaloGeo<GEO>::PITCH)
+  const int pitch = g2 ? 5 : (g1 ? 20 : HALO_W);      // pixels per halo-tile row (HaloGeo<GEO>::PITCH)
   if (stride == 2) {
     // Output (oy, ox) reads input (2 oy + ky - 1, 2 ox + kx - 1): ky = 1 is row oy of the even-row view, ky = 0 / 2 are
     // rows oy - 1 / oy of the odd-row view, likewise in x. So the conv is four small convs over the parity views, whose
@@ -191,13 +202,26 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       encode_src(i, a.ptr + ((size_t)py * a.W + px) * a.C, a.C, PW, PH, (size_t)2 * a.C, (size_t)2 * a.W * a.C,
                  (size_t)a.H * a.W * a.C);
       HaloSeg& sg = p.seg[i];
-      sg.map = i; sg.cblocks = a.C / CONV_BLOCK_K; sg.gn_off = -1;
+      sg.map = i; sg.cblocks = a.C / CONV_BLOCK_K; sg.gn_off = srcs[0].gn_off;      // (every view shares the channel table)
       sg.ntaps = S2[i][2]; sg.tap_w = S2[i][3]; sg.pix0 = pix0[i];
       sg.k_base = tap0 * a.C; sg.k_tap_stride = a.C;
       tap0 += sg.ntaps;
     }
+    any_gn |= srcs[0].gn_off >= 0;
     k_short = 9 * a.C;
     p.num_segs = 4;
+    // 1x1 stride-2 shortcut sources (arcface.py:133-137 downsample): input (2 oy, 2 ox) = the even / even view's centre tap
+    for (size_t i = 1; i < srcs.size(); ++i) {
+      const Act& r = srcs[i].act;
+      REQUIRE(srcs[i].ntaps == 1 && srcs[i].gn_off < 0 && r.B == out.B && r.H == a.H && r.W == a.W && r.C % CONV_BLOCK_K == 0,
+              "halo conv: a stride-2 shortcut source is a raw 1x1 over the conv's input grid");
+      encode_src(p.num_segs, r.ptr, r.C, PW, PH, (size_t)2 * r.C, (size_t)2 * r.W * r.C, (size_t)r.H * r.W * r.C);
+      HaloSeg& sg = p.seg[p.num_segs];
+      sg.map = p.num_segs; sg.cblocks = r.C / CONV_BLOCK_K; sg.gn_off = -1;
+      sg.ntaps = 1; sg.tap_w = 1; sg.pix0 = pitch + 1; sg.k_base = k_short; sg.k_tap_stride = 0;
+      k_short += r.C;
+      ++p.num_segs;
+    }
   } else
   for (size_t i = 0; i < srcs.size(); ++i) {
     const HaloSource& s = srcs[i];
@@ -235,8 +259,8 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   if (stride == 1) p.num_segs = (int)srcs.size();
   REQUIRE(k_short == w.k_total, "halo conv: packed weight K does not match the segment list");
   REQUIRE(w.up_folded == upsample2x, "halo conv: weight packing / upsample mismatch");
-  p.tiles_w = g1 ? 1 : PW / HALO_TW;
-  p.tiles_h = g1 ? 1 : PH / HALO_TH;
+  p.tiles_w = g1 ? 1 : (PW + HALO_TW - 1) / HALO_TW;
+  p.tiles_h = g1 ? 1 : (PH + HALO_TH - 1) / HALO_TH;
   p.units = (out.B + gi - 1) / gi;
   p.inv_tiles_w = 1.0f / (float)p.tiles_w; p.inv_tiles_h = 1.0f / (float)p.tiles_h;
   p.inv_num_par = 1.0f / (float)p.num_par; p.inv_units = 1.0f / (float)p.units;
@@ -245,8 +269,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.bias = bias; p.bias_t_stride = bias_t_stride; p.ctl = ctl;
   p.out = out.ptr;
   REQUIRE(!any_gn || gn_C <= 1024, "halo conv: the fused GroupNorm handles at most 1024 channels");
-  REQUIRE(!any_gn || gn_swish, "halo conv: the fused GroupNorm is always followed by Swish (unet.py:84-86)");
+  REQUIRE(!any_gn || gn_swish || prelu, "halo conv: the fused GroupNorm is always followed by Swish (unet.py:84-86)");
+  REQUIRE(!prelu || any_gn, "halo conv: PReLU slopes without a transformed source");
   p.gn = any_gn ? gn : nullptr; p.gn_C = gn_C; p.gn_swish = gn_swish ? 1 : 0;
+  p.gn_b_stride = prelu ? 0 : gn_C;
+  p.xf_slope = prelu_slope;
   if (any_gn && gn_from_stats) {
     const GnPlan& g = *gn_from_stats;
     REQUIRE(g.C0 + g.C1 == gn_C && g.HW == PH * PW && g.B == out.B, "halo conv: GroupNorm plan does not match the sources");
@@ -314,6 +341,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       if (c[2] == 2 && c[0] < cg_min_bn) continue;
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (is_head && c[0] != 64) continue;
+      if (prelu && (c[2] != 1 || (c[1] == 2 && c[0] != 64))) continue;      // instantiated: (64,1) (64,2) (128,1) (256,1)
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (g2 && c[0] != 64) continue;
       if (c[0] == 128 && c[1] == 2 && !allow_128x2) continue;
@@ -346,7 +374,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     for (int i = 0; i < p.num_segs; ++i) (p.seg[i].ntaps == 1 ? sc_blocks : main_blocks) += p.seg[i].cblocks;
     const char* e = getenv("B200SR3_HALO_DEEP");
     const int force = e ? atoi(e) : -1;
-    const bool can = !g1 && cg == 1 && !tail && !is_head && any_gn && stride == 1 && !upsample2x && (bn == 64 || bn == 128) &&
+    const bool can = !g1 && cg == 1 && !tail && !is_head && any_gn && !prelu && stride == 1 && !upsample2x && (bn == 64 || bn == 128) &&
                      !getenv("B200SR3_HALO_BN") && !getenv("B200SR3_HALO_MT");
     if (can && force != 0) {
       if (bn == 64 && (sc_blocks >= 2 || force == 1)) { deep = true; mt = 1; }
@@ -393,8 +421,13 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
     op.flops_executed = 2.0 * m * (double)out.C * k_exec;
   }
-  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head, deep](cudaStream_t s) {
-    if (deep) {
+  op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head, deep, prelu](cudaStream_t s) {
+    if (prelu) {
+      if (bn == 256) launch_pdl(conv_halo_kernel<256, 1, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(256)), HaloSmem<256, 1, 0, 1>::TOTAL, s, *pp);
+      else if (bn == 128) launch_pdl(conv_halo_kernel<128, 1, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(128)), HaloSmem<128, 1, 0, 1>::TOTAL, s, *pp);
+      else if (mt == 2) launch_pdl(conv_halo_kernel<64, 2, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 2, 0, 1>::TOTAL, s, *pp);
+      else launch_pdl(conv_halo_kernel<64, 1, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 0, 1>::TOTAL, s, *pp);
+    } else if (deep) {
       if (bn == 64) launch_pdl(conv_halo_kernel<64, 1, true, 0, 1, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 0, 1, true>::TOTAL, s, *pp);
       else launch_pdl(conv_halo_kernel<128, 1, true, 0, 1, false, true>, dim3(grid), dim3(halo_threads(128)), HaloSmem<128, 1, 0, 1, true>::TOTAL, s, *pp);
     } else if (is_head) {

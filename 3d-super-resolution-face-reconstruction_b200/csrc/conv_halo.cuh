@@ -62,7 +62,7 @@ constexpr int halo_threads(int block_n) { return 512 + 128 * (halo_esets(block_n
 constexpr int halo_a_stages(int block_n, int mt, int geo, bool deep = false) {
   return (deep && geo == 0 && mt == 1) ? (block_n == 64 ? 6 : (block_n == 128 ? 5 : 3)) : 3;
 }
-constexpr int HALO_MAX_SEGS = 4;
+constexpr int HALO_MAX_SEGS = 6;      // e.g. a stride-2 conv (four parity views) plus two shortcut sources
 
 // Tile geometry. GEO 0: an 8 x 16 pixel tile of one image, halo 10 x 18. GEO 1 (8 x 8 images): a tile is
 // TWO whole images laid side by side in the halo tile - pixel (hy, image, hx) at hy*20 + image*10 + hx,
@@ -126,6 +126,11 @@ struct alignas(64) ConvHaloParams {
   const float2* gn;                // [B][gn_C] (scale, shift) of the fused GroupNorm (null: none, or built in-kernel)
   int gn_C;
   int gn_swish;
+  int gn_b_stride;                 // float2 elements between consecutive images' rows of `gn` (0: one row for every image)
+  // PRELU (template flag): the transform is y = scale * prelu(x; slope) + shift per channel instead of GroupNorm + Swish
+  // - the BatchNorm / PReLU in front of a conv of the ArcFace iResNet (model/mica/arcface.py:58-66), whose zero
+  // padding must stay zero just like the UNet's. (scale, shift) come from `gn` (one row, gn_b_stride = 0).
+  const float* xf_slope;           // [gn_C] PReLU slopes (1 = no PReLU)
   // In-kernel (scale, shift) table: the transform warps turn the producers' per-channel partial sums
   // ([B][slots][C][2] int64 fixed point, as written by a conv epilogue) into the table of the current image themselves,
   // which removes the gn_scale_shift launch that otherwise sits between every two convs (same arithmetic, same bits).
@@ -402,7 +407,7 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
     for (int idx = tt; idx < IMGS * p.gn_C; idx += 256) {
       const int im = idx / p.gn_C;
       const int c = idx - im * p.gn_C;
-      float2 v = __ldg(p.gn + (size_t)min(b0 + im, p.B - 1) * p.gn_C + c);
+      float2 v = __ldg(p.gn + (size_t)min(b0 + im, p.B - 1) * p.gn_b_stride + c);
       if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
       gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
     }
@@ -416,10 +421,11 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
 // per MMA from (4 + N/32) KB to (4 + N/64) KB. The leader (rank 0) issues the MMAs; its barriers collect both CTAs'
 // weight loads (TMA in cta_group::2 form signals the leader's barrier), transform arrivals and epilogue releases;
 // tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
-template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = false, bool DEEP = false>
+template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = false, bool DEEP = false, bool PRELU = false>
 __global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   using S = HaloSmem<BLOCK_N, MT, GEO, CG, DEEP>;
+  static_assert(!PRELU || (FUSE_GN && GEO == 0 && CG == 1 && !HEAD && !DEEP && BLOCK_N != 16), "affine + PReLU transform: plain GEO 0 shapes");
   static_assert(!DEEP || (GEO == 0 && MT == 1 && CG == 1 && !HEAD && (BLOCK_N == 64 || BLOCK_N == 128)), "deep ring: one-tile shapes");
   static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
   static_assert(!HEAD || (!FUSE_GN && GEO == 0 && CG == 1 && BLOCK_N == 64), "the head conv is a raw 3x3, Cout = 64");
@@ -591,7 +597,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;
     tab_b_early = tile0.b;
     halo_build_gn_table<G::IMGS>(p, reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET), p.gn_C + 2 * (p.gn_C >> 3), tt,
-                                 tab_b_early, p.gn_swish != 0);
+                                 tab_b_early, !PRELU && p.gn_swish != 0);
     if (HALO_DBG && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
   }
   if (GEO == 2) {
@@ -1070,7 +1076,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;      // 0..255
     const int j = tt & 7;
     const int p_first = tt >> 3;
-    constexpr bool do_swish = true;      // Block = GroupNorm -> Swish -> Conv (unet.py:84-86): the host rejects a fused GroupNorm without Swish
+    constexpr bool do_swish = !PRELU;    // Block = GroupNorm -> Swish -> Conv (unet.py:84-86): the host rejects a fused GroupNorm without Swish
     float2* gtab = reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET);       // [IMGS][gn_C (padded)], halved if swish
     const int gn_pitch = p.gn_C + 2 * (p.gn_C >> 3);
     int tab_b = tab_b_early;
@@ -1082,7 +1088,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       Tile t[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m) { t[m] = walk; tile_next(walk); }
-      if (FUSE_GN && t[0].b != tab_b) {
+      if (FUSE_GN && (PRELU ? tab_b < 0 : t[0].b != tab_b)) {      // (the affine + PReLU table is the same for every image)
         halo_build_gn_table<G::IMGS>(p, gtab, gn_pitch, tt, t[0].b, do_swish);
         tab_b = t[0].b;
       }
@@ -1091,6 +1097,13 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         for (int cb = 0; cb < seg.cblocks; ++cb) {
           constexpr int NTAB = GEO == 2 ? 1 : IMGS;      // GEO 2 fetches (scale, shift) per pixel item instead
           float sc[NTAB][8], sh[NTAB][8];
+          float sl[PRELU ? 8 : 1];
+          if (PRELU && seg.gn_off >= 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.xf_slope + seg.gn_off + cb * CONV_BLOCK_K + j * 8);
+            const float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1);
+            sl[0] = s0.x; sl[1 % (PRELU ? 8 : 1)] = s0.y; sl[2 % (PRELU ? 8 : 1)] = s0.z; sl[3 % (PRELU ? 8 : 1)] = s0.w;
+            sl[4 % (PRELU ? 8 : 1)] = s1.x; sl[5 % (PRELU ? 8 : 1)] = s1.y; sl[6 % (PRELU ? 8 : 1)] = s1.z; sl[7 % (PRELU ? 8 : 1)] = s1.w;
+          }
           HDBG_T0();
           if (seg.gn_off >= 0 && GEO != 2) {
 #pragma unroll
@@ -1200,6 +1213,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                 for (int e = 0; e < 8; ++e) {
                   float scv = sc[0][e], shv = sh[0][e];
                   if (GEO == 1 && img[i] == 1) { scv = sc[NTAB - 1][e]; shv = sh[NTAB - 1][e]; }
+                  if (PRELU) {      // y = scale * prelu(x) + shift (arcface.py:60-64: bn1 before conv1, prelu before conv2)
+                    const float x = f[e];
+                    f[e] = fmaf(x > 0.f ? x : x * sl[e % (PRELU ? 8 : 1)], scv, shv);
+                    continue;
+                  }
                   const float h = fmaf(f[e], scv, shv);
                   // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
                   f[e] = do_swish ? fmaf(h, tanh_approx(h), h) : h;

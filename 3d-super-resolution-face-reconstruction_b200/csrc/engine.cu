@@ -43,8 +43,8 @@ static void pack_slice(const float* src, bf16* dst, int Cout, int cseg, int c0, 
   CUDA_CHECK(cudaGetLastError());
 }
 
-void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s) {
-  pack_slice(w, dst, Cout, Cin, 0, Cin, 9, Cin, 0, 9 * Cin, s, TAPS_BY_INPUT_PARITY);
+void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s, int k_total) {
+  pack_slice(w, dst, Cout, Cin, 0, Cin, 9, Cin, 0, k_total ? k_total : 9 * Cin, s, TAPS_BY_INPUT_PARITY);
 }
 
 // Identity block appended along K: out += 1.0 * x, i.e. the ResnetBlock's identity shortcut

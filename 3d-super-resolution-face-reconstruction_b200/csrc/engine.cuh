@@ -205,9 +205,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                      const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr,
                      const GnPlan* gn_from_stats = nullptr,    // non-null: the kernel builds the table itself (gn ignored)
                      int stride = 1,                           // 2: Downsample (unet.py:68-74), weights with down_perm
-                     const struct HaloHead* head = nullptr);   // non-null: downs.0 straight from the fp32 NCHW inputs
+                     const struct HaloHead* head = nullptr,    // non-null: downs.0 straight from the fp32 NCHW inputs
+                     const float* prelu_slope = nullptr,       // non-null: transform = `gn` row (scale, shift) + PReLU slopes
+                     bool partial_tiles = false);              // any H, W (no statistics): ArcFace's 56 / 28 / 14 / 7 px
 void conv_halo_init_device();
 // OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][9*Cin] with the taps in PackedConv::down_perm order (engine.cu)
-void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s);
+// (k_total > 9*Cin: the row also holds shortcut columns behind the taps)
+void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s, int k_total = 0);
 
 }  // namespace b200sr3

@@ -271,7 +271,8 @@ def main():
               "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no flush needed",
               "weights": "synthetic (numpy PCG64 seed 0), default-init scale"}
     if w["mica"]:
-        config["tail_stage"] = "each chain is followed by the SR->MICA hand-off kernels (tensor2img, resize 224, ArcFace blob)"
+        config["tail_stage"] = ("each chain is followed by the SR->MICA hand-off kernels (tensor2img, resize 224, ArcFace blob), "
+                                "the ArcFace iResNet-100, F.normalize and the MappingNetwork regressor (identity + shape code)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -313,7 +314,21 @@ def main():
     cond_host = cond_all[lo:hi].contiguous().pin_memory()
     cond = cond_host.to(dev)
     gather = HostGather((glob_b, 3, R, R))       # the one final gather lands here (pinned, mapped by every rank)
-    handoff_launches = 0
+    mica = None
+    if w["mica"]:
+        # config 5: "SR output feeding the MICA/FLAME recon stage end-to-end" - hand-off kernels, ArcFace iResNet-100,
+        # F.normalize and the MappingNetwork regressor on the device (the FLAME decoder needs licensed assets)
+        mica = b200sr3.MicaEncoder()
+        mica.arcface.load_state_dict(synthetic.mica_state_dict(mica.arcface, seed=1), strict=True)
+        mica.regressor.load_state_dict(synthetic.mica_state_dict(mica.regressor, seed=2), strict=True)
+        mica = mica.to(dev).eval()
+    mica_launches = [0]
+
+    def recon_stage(sr):
+        h = mica_handoff.sr_to_mica(sr)
+        ident, shape = mica(h["arcface"])
+        mica_launches[0] = 2 + 107
+        return shape
 
     def barrier():
         if world > 1:
@@ -325,7 +340,7 @@ def main():
         out = net.super_resolution_batched(cond, seed=1000 + i, row_offset=lo)
         gather.put(lo, out)                      # async D2H of this rank's slice: the final gather, no rendezvous
         if w["mica"]:
-            mica_handoff.sr_to_mica(out)
+            recon_stage(out)
         return out
 
     for i in range(args.warmup):
@@ -339,7 +354,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         one_chain(100 + i)
-        launches += net.launch_counts()[0] + (2 if w["mica"] else 0)
+        launches += net.launch_counts()[0] + mica_launches[0]
     e1.record()
     barrier()
     mine = e0.elapsed_time(e1) / 1e3
@@ -361,7 +376,7 @@ def main():
     for i in range(args.steps):
         net.sample_host(cond_host, out_rows, seed=200 + i, row_offset=lo)
         if w["mica"]:
-            mica_handoff.sr_to_mica(out_rows.to(dev, non_blocking=True))
+            recon_stage(out_rows.to(dev, non_blocking=True)).cpu()      # the shape codes are what leaves the device
     torch.cuda.synchronize()
     e2e_mine = time.perf_counter() - t0
     e2e_s = e2e_mine

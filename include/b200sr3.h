@@ -200,6 +200,42 @@ B200SR3_API int b200sr3_mica_handoff(const uint8_t* img, int B, int R, uint8_t* 
  * x fp32 NCHW [B,3,R,R] -> arcface_blob fp32 NCHW [B,3,112,112]; float path, parity within 1e-5. */
 B200SR3_API int b200sr3_tensor_blob(const float* x, int B, int R, float* arcface_blob, void* stream);
 
+/* ---- MICA identity encoder on the device: everything between the ArcFace blob above and the
+ * FLAME decoder. Replaces, for a whole batch,
+ *   codedict['arcface'] = F.normalize(self.arcface(arcface_imgs))      model/sr3d/model.py:164-170 (encode_mica)
+ *   shape = self.regressor(arcface)                                     model/mica/generator.py:86-88
+ * with self.arcface = Arcface() (iResNet-100, model/mica/arcface.py:165-200, eval mode: BatchNorm running statistics,
+ * no dropout) and self.regressor = MappingNetwork(z_dim, map_hidden_dim, n_shape, map_layers)
+ * (model/mica/generator.py:31-60; the reference builds it with 512 / 300 / 300 / 3, model/sr3d/model.py:68-75).
+ * The convs run in bf16 with fp32 accumulation; stated tolerance in tests/test_gpu_arcface.py.
+ *
+ * Weights: `key` is "arcface." + the reference Arcface state_dict key (e.g. "arcface.layer3.17.bn2.running_var") or
+ * "regressor." + the MappingNetwork key ("regressor.network.0.weight", "regressor.output.bias"); fp32, host or device,
+ * reference layouts. "...num_batches_tracked" entries are accepted and ignored. finalize folds every BatchNorm that
+ * follows a conv into that conv and packs the bf16 operands. */
+typedef struct b200sr3_mica b200sr3_mica;
+B200SR3_API int b200sr3_mica_create(int device, int z_dim, int map_hidden_dim, int map_layers, int n_shape,
+                   b200sr3_mica** out);
+B200SR3_API int b200sr3_mica_destroy(b200sr3_mica* h);
+B200SR3_API int b200sr3_mica_num_tensors(b200sr3_mica* h);
+B200SR3_API int b200sr3_mica_tensor_info(b200sr3_mica* h, int index, const char** key, int64_t shape[4], int* ndim);
+B200SR3_API int b200sr3_mica_load_tensor(b200sr3_mica* h, const char* key, const float* data, const int64_t* shape,
+                   int ndim);
+B200SR3_API int b200sr3_mica_finalize_weights(b200sr3_mica* h, void* stream);
+/* arcface_blob: fp32 [B,3,112,112] as b200sr3_mica_handoff / cv2.dnn.blobFromImages produce it (host or device).
+ * Outputs, each optional (NULL to skip), host or device: embedding [B,512] = Arcface.forward (arcface.py:179-200),
+ * identity [B,512] = F.normalize(embedding), shape_code [B,n_shape] = the regressor's output. */
+B200SR3_API int b200sr3_mica_encode(b200sr3_mica* h, const float* arcface_blob, int B, float* embedding,
+                   float* identity, float* shape_code, void* stream);
+/* Introspection for layer-level parity tests: the residual stream after "stem" or a block ("layer1.0" ... "layer4.2",
+ * arcface.py module names) of the most recent encode, as fp32 NCHW. */
+B200SR3_API int b200sr3_mica_layer_output(b200sr3_mica* h, const char* layer, float* dst, int* C, int* H, int* W,
+                   void* stream);
+/* Measurement aid: one eager pass with a CUDA event between launches (per-launch ms, algorithmic FLOPs, names) and
+ * the launch counts of the last encode. */
+B200SR3_API int b200sr3_mica_profile(b200sr3_mica* h, int B, int max_ops, float* ms, double* flops, char* names,
+                   int names_len, int* n_ops, int64_t* launches, int64_t* conv_launches, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,20 @@ def test_define_G_accepts_every_reference_yaml():
             assert mine["unet"]["channel_multiplier"] == list(opt["sr"]["model"]["unet"]["channel_multiplier"])
             assert mine["diffusion"] == dict(opt["sr"]["model"]["diffusion"])
         del net
+
+
+def test_mica_encoder_state_dict_contract():
+    """The drop-in Arcface / MappingNetwork carry the reference modules' keys and shapes (925 + 10 entries), and refuse
+    to compute on the CPU."""
+    from oracle import arcface_oracle as A
+    enc = b200sr3.MicaEncoder()
+    arc, mp = A.make_arcface_state_dict(0), A.make_mapping_state_dict(0)
+    own = enc.arcface.state_dict()
+    assert set(own) == set(arc) and all(tuple(own[k].shape) == tuple(arc[k].shape) for k in arc)
+    assert set(enc.regressor.state_dict()) == set(mp)
+    assert sum(p.numel() for p in enc.arcface.parameters()) == 65156160
+    enc.arcface.load_state_dict(arc, strict=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc.arcface(torch.zeros(1, 3, 112, 112))
+    with pytest.raises(NotImplementedError):
+        b200sr3.MappingNetwork(512, 300, 300, hidden=6)

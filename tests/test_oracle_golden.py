@@ -94,3 +94,21 @@ def test_headline_chain_steps_match_reference(golden_dir, fname):
         with torch.no_grad():
             out = O.p_sample(sd, mopt, tabs, state[T - 1 - t], t, cond, z)
         assert float((out - state[T - t]).abs().max()) <= TOL_STEP, (fname, t)
+
+
+def test_arcface_oracle_matches_reference(golden_dir):
+    """Case I (oracle/make_golden_arcface.py): iResNet-100 + F.normalize + MappingNetwork against the reference modules."""
+    import torch.nn.functional as F
+    from oracle import arcface_oracle as A
+    g = _load(golden_dir, "arcface_b2.npz")
+    arc, mp = A.make_arcface_state_dict(int(g["arcface_weight_seed"])), A.make_mapping_state_dict(int(g["mapping_weight_seed"]))
+    assert A.digest(arc) == str(g["arcface_sha256"]) and A.digest(mp) == str(g["mapping_sha256"])
+    blob = A.make_blob(2, seed=int(g["blob_seed"]))
+    assert hashlib.sha256(blob.numpy().tobytes()).hexdigest() == str(g["blob_sha256"])
+    with torch.no_grad():
+        emb = A.arcface_forward(arc, blob)
+        ident, shape = A.mica_encode(arc, mp, blob)
+    assert float((emb - torch.from_numpy(g["embedding"])).abs().max()) <= 1e-4
+    assert float((ident - torch.from_numpy(g["identity"])).abs().max()) <= 1e-6
+    assert float((shape - torch.from_numpy(g["shape_code"])).abs().max()) <= 1e-6
+    assert len(arc) == 925 and sum(v.numel() for k, v in arc.items() if "running" not in k and "tracked" not in k) == 65156160

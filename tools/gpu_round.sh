@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/${TAG}_gpu_tests.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.txt 2>&1
 python bench.py > gpurun_out/${TAG}_bench_line.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc $?"
+python bench.py --config sr_sr3_VGGF2_32_128_model2 --no-cpu-baseline --no-torch-baseline > gpurun_out/${TAG}_bench_line_cfg5.json 2>> gpurun_out/${TAG}_bench.err; echo "bench cfg5 rc $?"; head -c 900 gpurun_out/${TAG}_bench_line_cfg5.json; echo
 python tools/profile_step.py 32 128 600 > gpurun_out/${TAG}_step_profile_B32_R128.txt 2>&1
 if [ -n "$2" ]; then
   env "${@:2}" python bench.py --no-cpu-baseline --no-torch-baseline --no-parity > gpurun_out/${TAG}_bench_line_AB.json 2>> gpurun_out/${TAG}_bench.err
