@@ -421,30 +421,7 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       cudaEventDestroy(e1);
     }
     if (timing) {
-      std::vector<unsigned long long> h(256 * 16);
-      CUDA_CHECK(cudaMemcpy(h.data(), st.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      double acc[16] = {0};
-      int n = 0;
-      for (int c = 0; c < 256; ++c) {
-        if (h[c * 16 + 2] == 0) continue;
-        ++n;
-        for (int k = 0; k < 16; ++k) acc[k] += (double)h[c * 16 + k];
-      }
-      if (n) {
-        const double sup = acc[2] / n;
-        auto per = [&](int k) { return acc[k] / n / sup; };
-        fprintf(stderr,
-                "halo timing (avg over %d CTAs, %.1f super tiles each; cycles per super tile): total %.0f | A producer "
-                "waits empty %.0f | MMA waits A %.0f, W %.0f, TMEM %.0f | epilogue waits accum %.0f | transform waits "
-                "A full %.0f, works %.0f\n",
-                n, sup, per(1), per(0), per(4), per(5), per(6), per(8), per(10), per(11));
-        double mx14 = 0;
-        for (int c = 0; c < 256; ++c) mx14 = std::max(mx14, (double)h[c * 16 + 14]);
-        fprintf(stderr, "  per CTA (cycles): entry -> prologue done %.0f | -> GroupNorm table ready %.0f | -> first halo landed %.0f\n",
-                acc[15] / n, acc[3] / n, acc[7] / n);
-        fprintf(stderr, "  per CTA (cycles): entry -> first MMA %.0f | entry -> last MMA issued %.0f | entry -> epilogue done %.0f "
-                        "(slowest CTA %.0f)\n", acc[12] / n, acc[13] / n, acc[14] / n, mx14);
-      }
+      halo_report_timing(st.dbg, nullptr);
     }
   });
 }

@@ -1,7 +1,9 @@
 // Host side of the halo-resident convolution (conv_halo.cuh): tensor maps, segment list, tile-shape
 // choice, launch closure.
+#include <cstdio>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -72,6 +74,34 @@ static void launch_halo_pair(const ConvHaloParams& p, bool gn, int grid, cudaStr
   cfg.numAttrs = 1;
   if (gn) CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, 1, true, 0, 2>, p));
   else CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, 1, false, 0, 2>, p));
+}
+
+// Role counters of one launch (timing build, conv_halo.cuh HALO_DBG): averages over the CTAs that ran tiles.
+void halo_report_timing(const unsigned long long* dbg_dev, const char* label) {
+  std::vector<unsigned long long> h(256 * 16);
+  CUDA_CHECK(cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  double acc[16] = {0};
+  int n = 0;
+  for (int c = 0; c < 256; ++c) {
+    if (h[c * 16 + 2] == 0) continue;
+    ++n;
+    for (int k = 0; k < 16; ++k) acc[k] += (double)h[c * 16 + k];
+  }
+  if (!n) return;
+  const double sup = acc[2] / n;
+  auto per = [&](int k) { return acc[k] / n / sup; };
+  if (label) fprintf(stderr, "[%s] ", label);
+  fprintf(stderr,
+          "halo timing (avg over %d CTAs, %.1f super tiles each; cycles per super tile): total %.0f | A producer "
+          "waits empty %.0f | MMA waits A %.0f, W %.0f, TMEM %.0f | epilogue waits accum %.0f | transform waits "
+          "A full %.0f, works %.0f\n",
+          n, sup, per(1), per(0), per(4), per(5), per(6), per(8), per(10), per(11));
+  double mx14 = 0;
+  for (int c = 0; c < 256; ++c) mx14 = std::max(mx14, (double)h[c * 16 + 14]);
+  fprintf(stderr, "  per CTA (cycles): entry -> prologue done %.0f | -> GroupNorm table ready %.0f | -> first halo landed %.0f\n",
+          acc[15] / n, acc[3] / n, acc[7] / n);
+  fprintf(stderr, "  per CTA (cycles): entry -> first MMA %.0f | entry -> last MMA issued %.0f | entry -> epilogue done %.0f "
+                  "(slowest CTA %.0f)\n", acc[12] / n, acc[13] / n, acc[14] / n, mx14);
 }
 
 static bool geo1(int H, int W) { return H == 8 && W == 8; }   // two whole 8x8 images per tile
@@ -400,10 +430,11 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   p.pdl = pdl_enabled() ? 1 : 0;
   if (stats) p.dbg = stats->dbg;
   if (stats && stats->partial) {
-    REQUIRE(cg * slots_needed(p.seg_len_super, p.total_super, grid / cg) <= stats->slots,
+    REQUIRE(stats->atomic ? stats->slots == 1 : cg * slots_needed(p.seg_len_super, p.total_super, grid / cg) <= stats->slots,
             "halo conv: statistics scratch has too few slots");
     p.stat_partial = stats->partial;
     p.stat_slots = stats->slots;
+    p.stat_atomic = stats->atomic ? 1 : 0;
   }
 
   Op op;
@@ -448,6 +479,25 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     else if (mt == 2) launch_halo<16, 2>(*pp, any_gn, grid, s);
     else launch_halo<16, 1>(*pp, any_gn, grid, s);
   };
+#if B200SR3_ROLE_TIMING
+  // timing build: role counters of the launches named in B200SR3_TIMING_OPS ("all" or a comma-separated list of op
+  // names), printed by Engine::profile_step (tools/profile_step.py)
+  if (const char* sel = getenv("B200SR3_TIMING_OPS")) {
+    const std::string list = std::string(",") + sel + ",";
+    if (std::string(sel) == "all" || list.find("," + name + ",") != std::string::npos) {
+      unsigned long long* buf = nullptr;
+      CUDA_CHECK(cudaMalloc(&buf, 256 * 16 * sizeof(unsigned long long)));
+      CUDA_CHECK(cudaMemset(buf, 0, 256 * 16 * sizeof(unsigned long long)));
+      std::shared_ptr<unsigned long long> hold(buf, [](unsigned long long* q) { cudaFree(q); });
+      pp->dbg = buf;
+      const std::string label = name;
+      op.report = [hold, label]() {
+        halo_report_timing(hold.get(), label.c_str());
+        cudaMemset(hold.get(), 0, 256 * 16 * sizeof(unsigned long long));
+      };
+    }
+  }
+#endif
   if (params_out) *params_out = pp;
   return op;
 }

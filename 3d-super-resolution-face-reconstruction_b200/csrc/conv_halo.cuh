@@ -141,6 +141,12 @@ struct alignas(64) ConvHaloParams {
   const float* gn_beta;
   long long* stat_partial;         // as ConvParams::stat_partial
   int stat_slots;
+  // stat_atomic: one [B][Cout][2] accumulator (stat_slots == 1), zeroed once per sampling step by the engine, that every
+  // CTA adds its int64 fixed-point sums into (RED.64). Integer addition is associative, so the result is as
+  // batch-invariant as the slot scheme, and the CONSUMER's GroupNorm table needs one load per channel instead of a chain
+  // of `slots` dependent L2 round trips (role counters, profiles/r02i_roles_in_situ.txt: 10-13 k cycles to the table
+  // with 5-6 slots - the largest single piece of every GroupNorm conv's fill time).
+  int stat_atomic;
   // BLOCK_N == 16 ("tail"): the conv is final_conv (unet.py:233, Cout = out_channel <= 4 padded to 16) and
   // the epilogue applies the sampler update (diffusion.py:144-187) to the fp32 NCHW state instead of
   // storing an activation: eps -> x0 = clamp(A x - B eps) -> mean -> + sigma z.
@@ -1053,6 +1059,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
             for (int ww = 0; ww < 4 * ESETS; ++ww)
               a += reinterpret_cast<const long long*>(smem_gen + S::STG_OFFSET + ww * (NSTG * 4096))[item];
+            if (p.stat_atomic) {
+              atomicAdd(reinterpret_cast<unsigned long long*>(p.stat_partial + ((size_t)(t0.b + im) * p.Cout + n0) * 2 + within),
+                        (unsigned long long)a);
+              continue;
+            }
             long long* dst = p.stat_partial + (((size_t)(t0.b + im) * p.stat_slots + slot) * p.Cout + n0) * 2 + within;
             *dst = a;
             if (is_last)

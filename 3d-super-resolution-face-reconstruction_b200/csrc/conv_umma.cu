@@ -236,9 +236,10 @@ Op make_conv_op(const std::string& name, const ConvSource& main, const Act* res0
       const int last_cta = (int)((((seg + 1) * p.seg_len) * G - 1) / T);
       need = std::max(need, last_cta - first_cta + 1);
     }
-    REQUIRE(need <= stats->slots, "conv: statistics scratch has too few slots");
+    REQUIRE(stats->atomic ? stats->slots == 1 : need <= stats->slots, "conv: statistics scratch has too few slots");
     p.stat_partial = stats->partial;
     p.stat_slots = stats->slots;
+    p.stat_atomic = stats->atomic ? 1 : 0;
   }
 
   Op op;

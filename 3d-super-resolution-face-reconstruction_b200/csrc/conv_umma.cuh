@@ -65,6 +65,7 @@ struct alignas(64) ConvParams {
   // CTAs - i.e. not on the batch size either: a face's result is bit-identical in any batch.
   long long* stat_partial;
   int stat_slots;
+  int stat_atomic;      // as ConvHaloParams::stat_atomic: one accumulator, added to with RED.64, zeroed by the engine
   int seg_len;                     // tiles per (n tile, image[-pair]) segment = tiles_w*tiles_h*num_par
   // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv2d): [grid][8] cycle counters
   unsigned long long* dbg;
@@ -560,7 +561,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             long long a = 0;
             for (int ww = 0; ww < wpi; ++ww) a += sstat[((ib * wpi + ww) * 2 + st) * BLOCK_N + col];
             const int bi = t.b0 + ib;
-            if (bi < p.B) {
+            if (bi < p.B && p.stat_atomic) {
+              atomicAdd(reinterpret_cast<unsigned long long*>(p.stat_partial + ((size_t)bi * p.Cout + (n0 + col)) * 2 + st),
+                        (unsigned long long)a);
+            } else if (bi < p.B) {
               long long* dst = p.stat_partial + (((size_t)bi * p.stat_slots + slot) * p.Cout + (n0 + col)) * 2 + st;
               *dst = a;
               if ((int)blockIdx.x == last_cta)

@@ -472,12 +472,38 @@ void Engine::build_workspace(Workspace& ws) {
     ws.bytes += bytes;
     return p;
   };
+  // GroupNorm statistics. Default: ONE [B][C][2] int64 accumulator per tensor, carved out of one arena that the first op
+  // of the step zeroes; the producing conv's CTAs add into it (ConvStats::atomic). B200SR3_STAT_SLOTS=1: the earlier
+  // scheme - one slot per producing CTA, written not added, summed by the consumer (for A/B).
+  static const bool stat_slots_mode = [] { const char* e = getenv("B200SR3_STAT_SLOTS"); return e && e[0] == '1'; }();
+  const bool stat_atomic = !stat_slots_mode;
+  size_t arena_cap = 0;
+  {
+    size_t ch = 4096;
+    for (const LayerDesc& l : layers_) ch += (size_t)(l.kind == LayerKind::Res ? (l.attn ? 12 : 4) : 2) * std::max(l.cout, l.c_x + l.c_skip) + 512;
+    arena_cap = ch * (size_t)B * 2 * sizeof(long long);
+  }
+  uint8_t* arena = stat_atomic ? (uint8_t*)dalloc(arena_cap) : nullptr;
+  auto arena_used = std::make_shared<size_t>(0);
+  if (stat_atomic) {
+    ws.ops.push_back(Op{"stats.zero", false, [arena, arena_used](cudaStream_t s) {
+      CUDA_CHECK(cudaMemsetAsync(arena, 0, *arena_used, s));
+    }});
+  }
   auto act = [&](int H, int W, int C, int stat_slots = 1) {
     Act a;
     a.B = B; a.H = H; a.W = W; a.C = C;
     a.ptr = (bf16*)dalloc(a.elems() * sizeof(bf16));
-    a.stat_slots = stat_slots;
-    a.stats = (long long*)dalloc((size_t)B * stat_slots * C * 2 * sizeof(long long));
+    if (stat_atomic) {
+      const size_t bytes = ((size_t)B * C * 2 * sizeof(long long) + 255) / 256 * 256;
+      REQUIRE(*arena_used + bytes <= arena_cap, "internal: statistics arena too small");
+      a.stat_slots = 1;
+      a.stats = reinterpret_cast<long long*>(arena + *arena_used);
+      *arena_used += bytes;
+    } else {
+      a.stat_slots = stat_slots;
+      a.stats = (long long*)dalloc((size_t)B * stat_slots * C * 2 * sizeof(long long));
+    }
     return a;
   };
   const int oc = cfg_.out_channel;
@@ -532,6 +558,7 @@ void Engine::build_workspace(Workspace& ws) {
     ConvStats st;
     st.partial = y.stats;
     st.slots = y.stat_slots;
+    st.atomic = stat_atomic;
     ws.ops.push_back(make_conv_op(name, cs, r0, r1, w, bias, bias_stride, ctl_, residual, y, force_block_n_,
                                   fuse ? &st : nullptr));
     ws.n_conv++;
@@ -574,6 +601,7 @@ void Engine::build_workspace(Workspace& ws) {
     ConvStats st;
     st.partial = y.stats;
     st.slots = y.stat_slots;
+    st.atomic = stat_atomic;
     ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, true,
                                        want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get(), stride));
     ws.n_conv++;
@@ -610,6 +638,7 @@ void Engine::build_workspace(Workspace& ws) {
             ConvStats st;
             st.partial = cur.stats;
             st.slots = cur.stat_slots;
+            st.atomic = stat_atomic;
             ws.ops.push_back(make_conv_halo_op(l.name, {HaloSource{virt, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0,
                                                ctl_, cur, nullptr, 0, true, &st, nullptr, nullptr, nullptr, 1, &hh));
             ws.n_conv++;
@@ -749,7 +778,7 @@ void Engine::write_ctl(int t, int mode, const float* noise, uint64_t seed, long 
 
 void Engine::run_ops(Workspace& ws, cudaStream_t s) {
   for (auto& op : ws.ops) op.run(s);
-  last_total += (int64_t)ws.ops.size();
+  last_total += ws.n_kernels();
   last_conv += ws.n_conv;
 }
 
@@ -793,6 +822,9 @@ int Engine::profile_step(int B, int R, int max_ops, float* ms, double* flops, do
       CUDA_CHECK(cudaEventRecord(ev[i + 1], s));
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
+    if (rep == 1)
+      for (auto& op : ws.ops)
+        if (op.report) op.report();      // timing build: role counters (accumulated "waits" are per super tile either way)
   }
   std::string all;
   for (int i = 0; i < n; ++i) {
@@ -892,7 +924,7 @@ void Engine::sample(const float* cond, int noise_mode, const float* noise, uint6
   for (int t = T - 1; t >= 0; --t) {
     if (ws.graph) {
       CUDA_CHECK(cudaGraphLaunch(ws.graph, s));
-      last_total += (int64_t)ws.ops.size() + 1;
+      last_total += ws.n_kernels() + 1;
       last_conv += ws.n_conv;
     } else {
       run_ops(ws, s);

@@ -56,6 +56,7 @@ struct Op {
   double flops = 0.0;   // algorithmic FLOPs (2*MAC on the reference graph) of one launch
   double bytes = 0.0;   // algorithmic HBM bytes of one launch (HBM-bound kernels)
   double flops_executed = 0.0;   // what the tensor pipe runs: + identity-shortcut segments and K padding, - upsample folding
+  std::function<void()> report;  // timing build only: prints (and resets) the launch's role counters
 };
 
 class Engine;
@@ -79,6 +80,11 @@ struct Workspace {
   std::map<std::string, Act> layer_out;
   cudaGraphExec_t graph = nullptr;
   int64_t n_conv = 0;
+  int64_t n_kernels() const {      // launches of the step that are kernels ("stats.zero" is a memset node)
+    int64_t n = 0;
+    for (const Op& op : ops) n += op.name != "stats.zero";
+    return n;
+  }
   ~Workspace();
 };
 
@@ -170,6 +176,7 @@ struct ConvSource {
 struct ConvStats {    // where the epilogue leaves the GroupNorm statistics of the output
   long long* partial = nullptr;   // [B][slots][Cout][2], 2^-24 fixed point
   int slots = 0;
+  bool atomic = false;            // slots == 1 and the launches ADD into it (the caller zeroes it once per step)
   unsigned long long* dbg = nullptr;   // role timing counters [148][8] (measurement only)
 };
 bool conv_can_fuse_stats(const Act& out, bool upsample2x);
@@ -209,6 +216,7 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                      const float* prelu_slope = nullptr,       // non-null: transform = `gn` row (scale, shift) + PReLU slopes
                      bool partial_tiles = false);              // any H, W (no statistics): ArcFace's 56 / 28 / 14 / 7 px
 void conv_halo_init_device();
+void halo_report_timing(const unsigned long long* dbg_dev, const char* label);
 // OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][9*Cin] with the taps in PackedConv::down_perm order (engine.cu)
 // (k_total > 9*Cin: the row also holds shortcut columns behind the taps)
 void pack_conv_weight_by_input_parity(const float* w, bf16* dst, int Cout, int Cin, cudaStream_t s, int k_total = 0);
