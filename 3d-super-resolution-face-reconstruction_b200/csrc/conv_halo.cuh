@@ -810,49 +810,56 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     int it = 0;
     HDBG_DECL();
     Tile walk = tile0;
+    const long long row0 = p.tail_x ? p.ctl->row0 : 0;
+    const unsigned long long seed = p.tail_x ? p.ctl->seed : 0ull;
+    const float* zp = nullptr;                      // injected noise of this step (modes 1 and 3), null: none
+    if (p.tail_x && ts > 0 && (mode == 1 || mode == 3) && p.ctl->noise)
+      zp = p.ctl->noise + (mode == 1 ? (size_t)(T - ts) * (size_t)p.ctl->numel : (size_t)0);
+    float bias_o[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) bias_o[o] = (p.bias && o < OC) ? __ldg(p.bias + o) : 0.f;
     for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
+      // Everything that does not depend on the accumulator happens BEFORE the wait for it: the state x and the injected
+      // noise of this thread's MT pixels are requested (L2 round trips of ~1 k cycles in situ; read inside the update
+      // loop they were serialised behind each other by the in-place stores) and the Philox / Box-Muller draws are made.
+      size_t base[MT];
+      float xv[MT][4], z[MT][4];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const Tile t = walk;
+        tile_next(walk);
+        const int y = t.y0 + ly, x = t.x0 + lx;
+        base[m] = (size_t)t.b * OC * plane + (size_t)y * p.W + x;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          xv[m][o] = (p.tail_x && o < OC) ? p.tail_x[base[m] + o * plane] : 0.f;
+          z[m][o] = (zp && o < OC) ? __ldg(zp + base[m] + o * plane) : 0.f;
+        }
+        if (p.tail_x && ts > 0 && mode == 2) {
+          const long long pix = ((row0 + (long long)t.b) * p.H + y) * p.W + x;      // global row: sharding-invariant noise
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+          const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
+          z[m][0] = g0.x; z[m][1] = g0.y; z[m][2] = g1.x; z[m][3] = g1.y;
+        }
+      }
       HDBG_T0();
       ptx::mbar_wait(tmem_full(buf), use & 1u);
       HDBG_ACC(0);
       ptx::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const Tile t = walk;
-        tile_next(walk);
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * MT + m) * BLOCK_N), v);
         ptx::tmem_ld_wait();
-        const int y = t.y0 + ly, x = t.x0 + lx;
-        const size_t base = (size_t)t.b * OC * plane + (size_t)y * p.W + x;
-        const long long pix = ((p.ctl->row0 + (long long)t.b) * p.H + y) * p.W + x;      // global row: sharding-invariant noise
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.tail_x && ts > 0) {
-          if (mode == 1 || mode == 3) {
-            const float* zp = p.ctl->noise;
-            if (zp) {
-              if (mode == 1) zp += (size_t)(T - ts) * (size_t)p.ctl->numel;
-#pragma unroll
-              for (int o = 0; o < 4; ++o) if (o < OC) z[o] = __ldg(zp + base + o * plane);
-            }
-          } else if (mode == 2) {
-            const unsigned long long seed = p.ctl->seed;
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)pix, (uint32_t)(pix >> 32), (uint32_t)ts, 0x5352u),
-                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
-            z[0] = g0.x; z[1] = g0.y; z[2] = g1.x; z[3] = g1.y;
-          }
-        }
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           if (o < OC) {
-            const float eps = __uint_as_float(v[o]) + (p.bias ? __ldg(p.bias + o) : 0.f);
-            if (p.tail_eps) p.tail_eps[base + o * plane] = eps;
-            if (p.tail_x) {
-              const float xv = p.tail_x[base + o * plane];
-              p.tail_x[base + o * plane] = posterior_update(xv, eps, z[o], a, bc, c1, c2, sigma, lim);
-            }
+            const float eps = __uint_as_float(v[o]) + bias_o[o];
+            if (p.tail_eps) p.tail_eps[base[m] + o * plane] = eps;
+            if (p.tail_x) p.tail_x[base[m] + o * plane] = posterior_update(xv[m][o], eps, z[m][o], a, bc, c1, c2, sigma, lim);
           }
         }
       }
