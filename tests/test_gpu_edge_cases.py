@@ -91,6 +91,26 @@ def test_attention_with_256_tokens_on_a_down_and_up_level():
     _close(net.unet_eps(cond.cuda(), noise[0].cuda(), 0.5).cpu(), ref)
 
 
+@pytest.mark.parametrize("inner,mults,groups,res_blocks,R", [(128, [1, 2], 16, 1, 32), (64, [1, 2, 2], 32, 3, 64), (192, [1], 32, 2, 16)])
+def test_other_unet_hyper_parameters(inner, mults, groups, res_blocks, R):
+    """define_G reads inner_channel / channel_multiplier / norm_groups / res_blocks from the YAML (networks.py:91-101);
+    every shipped config uses 64 / [1,2,4,8,8] / 32 / 2, the engine must not depend on that."""
+    mopt = copy.deepcopy(SMALL)
+    mopt["unet"].update(inner_channel=inner, channel_multiplier=mults, norm_groups=groups, res_blocks=res_blocks, attn_res=[])
+    mopt["diffusion"]["image_size"] = R
+    sd = make_state_dict(mopt, seed=inner, gain=1.1)
+    net, mopt = _build(mopt, sd)
+    cond, noise = make_inputs(3, R, 2, seed=inner + 1)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, mopt, torch.cat([cond, noise[0]], 1), torch.full((3, 1), 0.4))
+    _close(net.unet_eps(cond.cuda(), noise[0].cuda(), 0.4).cpu(), ref)
+    tabs = O.schedule_tables(mopt["beta_schedule"]["val"])
+    with torch.no_grad():
+        want = O.p_sample(sd, mopt, tabs, noise[0], 7, cond, noise[1])
+    got = net.p_sample(noise[0].cuda(), 7, condition_x=cond.cuda(), noise=noise[1].cuda()).cpu()
+    assert float((got - want).abs().max()) <= 2e-3
+
+
 def test_unconditional_sample_and_clip_flag(golden_dir):
     """diffusion.py:193-200: sample(batch_size, continous) on a conditional=False model; the list starts with x_T."""
     g = np.load(os.path.join(golden_dir, "uncond_r16_T20.npz"))
