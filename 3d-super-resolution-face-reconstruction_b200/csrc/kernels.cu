@@ -841,8 +841,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const bf16* _
 // elements against bank conflicts), S = Q K^T runs on mma.sync (bf16 in, fp32 out: a 0.01%-of-FLOPs
 // op, the legacy tensor path is plenty), the softmax is fp32, P is rounded to bf16 and O = P V reuses
 // K's buffer for V.
-__global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                            int HW, int C) {
+constexpr int ATT_MMA_THREADS = 256;      // 8 warps: the kernel is bound by the latency of staging K and V (2 x 64 KB per CTA)
+__global__ void __launch_bounds__(ATT_MMA_THREADS) attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                        int HW, int C) {
+  constexpr int NT = ATT_MMA_THREADS, NW = ATT_MMA_THREADS / 32;
   pdl_launch_dependents();
   pdl_wait();
   using namespace nvcuda;
@@ -852,23 +854,23 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
   bf16* kv_s = q_s + 16 * ld;                                  // [HW][ld]
   float* s_s = reinterpret_cast<float*>(kv_s + (size_t)HW * ld);   // [16][HW]
   bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * HW);          // [16][HW]
-  float* scr = reinterpret_cast<float*>(p_s + 16 * HW);        // [4][256]
+  float* scr = reinterpret_cast<float*>(p_s + 16 * HW);        // [NW][256]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * 16;
   const size_t row = (size_t)3 * C;
   const bf16* base = qkv + (size_t)b * HW * row;
   const int cv = C >> 3;
-  for (int i = tid; i < 16 * cv; i += 128) {
+  for (int i = tid; i < 16 * cv; i += NT) {
     const int r = i / cv, c = i - r * cv;
     *reinterpret_cast<uint4*>(q_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(q0 + r) * row + c * 8));
   }
-  for (int i = tid; i < HW * cv; i += 128) {
+  for (int i = tid; i < HW * cv; i += NT) {
     const int r = i / cv, c = i - r * cv;
     *reinterpret_cast<uint4*>(kv_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * row + C + c * 8));
   }
   __syncthreads();
   // ---- S = Q K^T: one 16x16 tile of keys per warp pass
-  for (int t = warp; t < HW / 16; t += 4) {
+  for (int t = warp; t < HW / 16; t += NW) {
     wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
     wmma::fill_fragment(acc, 0.f);
     for (int k = 0; k < C; k += 16) {
@@ -882,11 +884,11 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
   }
   __syncthreads();
   // ---- V replaces K while the softmax runs
-  for (int i = tid; i < HW * cv; i += 128) {
+  for (int i = tid; i < HW * cv; i += NT) {
     const int r = i / cv, c = i - r * cv;
     *reinterpret_cast<uint4*>(kv_s + r * ld + c * 8) = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * row + 2 * C + c * 8));
   }
-  {
+  if (tid < 128) {
     // 8 lanes per query row (unet.py:133-135: scores / sqrt(C), softmax over all keys)
     const int r = tid >> 3, sub = tid & 7;
     const float scale = rsqrtf((float)C);
@@ -907,7 +909,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
   __syncthreads();
   // ---- O = P V: 16-channel tiles round-robin over the warps
   float* my = scr + warp * 256;
-  for (int t = warp; t < C / 16; t += 4) {
+  for (int t = warp; t < C / 16; t += NW) {
     wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
     wmma::fill_fragment(acc, 0.f);
     for (int k = 0; k < HW; k += 16) {
@@ -928,13 +930,13 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const bf16* __restri
 void launch_attention(const bf16* qkv, bf16* out, int B, int HW, int C, cudaStream_t s) {
   REQUIRE(C % 8 == 0 && C <= 1024, "attention: C must be a multiple of 8 and <= 1024");
   if (HW % 16 == 0 && HW <= 64 && C % 16 == 0) {
-    const size_t smem = (size_t)(16 + HW) * (C + 8) * 2 + (size_t)16 * HW * 4 + (size_t)16 * HW * 2 + 4 * 256 * 4;
+    const size_t smem = (size_t)(16 + HW) * (C + 8) * 2 + (size_t)16 * HW * 4 + (size_t)16 * HW * 2 + (ATT_MMA_THREADS / 32) * 256 * 4;
     static bool attr_set = false;
     if (!attr_set) {
       CUDA_CHECK(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    launch_pdl(attention_mma_kernel, dim3(HW / 16, B), dim3(128), smem, s, qkv, out, HW, C);
+    launch_pdl(attention_mma_kernel, dim3(HW / 16, B), dim3(ATT_MMA_THREADS), smem, s, qkv, out, HW, C);
     CUDA_CHECK(cudaGetLastError());
     return;
   }
