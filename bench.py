@@ -440,13 +440,22 @@ def main():
             gbs = by / (ms * 1e-3) / 1e9
             hbm.append({"kernel": name, "us": ms * 1e3, "algorithmic_mb": by / 1e6, "achieved": gbs,
                         "frac": gbs / peaks["hbm_gbs"], "share_of_step": ms / step_ms})
+    hbm_traffic = None
+    try:      # DRAM bytes of the head and tail launches from the newest committed ncu capture (tools/profile_hbm_ends.sh)
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic_hbm.json")))
+        with open(files[-1]) as f:
+            tj = json.load(f)
+        hbm_traffic = {"file": os.path.basename(files[-1]), "this_build": tj.get("build_digest") == build_digest(),
+                       "dram_bytes_per_launch": {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}}
+    except Exception:
+        pass
     hbm_ms = sum(h["us"] for h in hbm) / 1e3
     hbm_bytes = sum(h["algorithmic_mb"] for h in hbm) * 1e6
     roofline_hbm = {"bound": "hbm", "kernel": "head (downs.0: fp32 NCHW cond/x -> 64-ch bf16), tail (final_conv + sampler "
                                               "update), attention GroupNorm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
                     "achieved": hbm_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None,
                     "frac": hbm_bytes / (hbm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if hbm_ms else None,
-                    "ms_per_step": hbm_ms, "share_of_step": hbm_ms / step_ms, "traffic": None, "kernels": hbm}
+                    "ms_per_step": hbm_ms, "share_of_step": hbm_ms / step_ms, "traffic": hbm_traffic, "kernels": hbm}
     ranks_ms = sorted(1e3 * s / args.steps for s in per_rank)
     line = {"metric": metric_name(w), "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
