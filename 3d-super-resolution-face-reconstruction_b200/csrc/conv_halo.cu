@@ -98,8 +98,8 @@ void halo_report_timing(const unsigned long long* dbg_dev, const char* label) {
           n, sup, per(1), per(0), per(4), per(5), per(6), per(8), per(10), per(11));
   double mx14 = 0;
   for (int c = 0; c < 256; ++c) mx14 = std::max(mx14, (double)h[c * 16 + 14]);
-  fprintf(stderr, "  per CTA (cycles): entry -> prologue done %.0f | -> GroupNorm table ready %.0f | -> first halo landed %.0f\n",
-          acc[15] / n, acc[3] / n, acc[7] / n);
+  fprintf(stderr, "  per CTA (cycles): entry -> prologue done %.0f | -> GroupNorm table: first barrier passed %.0f, ready %.0f | -> first halo landed %.0f\n",
+          acc[15] / n, acc[9] / n, acc[3] / n, acc[7] / n);
   fprintf(stderr, "  per CTA (cycles): entry -> first MMA %.0f | entry -> last MMA issued %.0f | entry -> epilogue done %.0f "
                   "(slowest CTA %.0f)\n", acc[12] / n, acc[13] / n, acc[14] / n, mx14);
 }

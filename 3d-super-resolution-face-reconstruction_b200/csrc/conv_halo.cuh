@@ -318,9 +318,107 @@ __device__ __forceinline__ void halo_head_row(const float* v, float* row) {
 // on its batch or tile. Statistics are read through L2 only (nothing stale in L1 under programmatic dependent launch).
 template <int IMGS>
 __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, float2* gtab, int gn_pitch, int tt, int b0,
-                                                    bool do_swish) {
+                                                    bool do_swish, long long t_entry = 0) {
   asm volatile("bar.sync 2, 256;" ::: "memory");      // everyone is done with the previous table
-  if (p.gn_stats0) {
+  if (HALO_DBG && tt == 0 && t_entry) p.dbg[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - t_entry);   // [9] table: past the first barrier
+  if (p.gn_stats0 && IMGS == 5) {
+    // Five images per tile (4x4 level): 160 (image, group) pairs over 256 lanes leave one lane per group, which then
+    // walked its 16-32 channels' statistics four at a time - 4 to 8 dependent L2 round trips, 14 k (C = 512) to 33 k
+    // (C = 1024) cycles in front of the first MMA (profiles/r02x_roles_R64.txt). Channel-parallel instead, three phases
+    // over shared memory: (1) lane -> channels tt + 256 j, all five images: load the sums (ten independent loads in
+    // flight per round, gamma / beta requested with the first round), park them as floats in the channel's table slot;
+    // (2) lane -> (image, group): mean and 1/std from the parked sums, in channel order (fixed summation order: batch-
+    // invariant); (3) lane -> its channels again: (scale, shift) over the slot. No integer division anywhere: with
+    // `idx / C` per item the index arithmetic alone cost ~500 cycles per item (measured: 11 k cycles for C = 512).
+    const int C = p.gn_C, C0 = p.gn_C0;
+    const int cg = C / p.gn_groups;
+    const float inv_cg = 1.0f / (float)cg;
+    float2* gstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(gtab) + IMGS * 1024 * 10);
+    float gm[4], bt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tt + 256 * j;
+      gm[j] = c < C ? __ldg(p.gn_gamma + c) : 0.f;
+      bt[j] = c < C ? __ldg(p.gn_beta + c) : 0.f;
+    }
+    // statistics of (image im, channel c): slot 0 at base + im * img_stride (images past the batch repeat the last one)
+    auto chan_base = [&](int c, int& slots, int& stride, size_t& img_stride) {
+      const bool second = c >= C0;
+      const int cs = second ? C - C0 : C0, cl = second ? c - C0 : c;
+      slots = second ? p.gn_slots1 : p.gn_slots0;
+      stride = cs * 2;
+      img_stride = (size_t)slots * cs * 2;
+      return (second ? p.gn_stats1 : p.gn_stats0) + (size_t)b0 * img_stride + (size_t)cl * 2;
+    };
+    const int last_im = min(IMGS - 1, p.B - 1 - b0);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (tt + 512 * half >= C) break;
+      longlong2 v[2][IMGS];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c = tt + 256 * (2 * half + jj);
+        int slots, stride;
+        size_t img_stride;
+        const long long* base = chan_base(min(c, C - 1), slots, stride, img_stride);
+#pragma unroll
+        for (int im = 0; im < IMGS; ++im)
+          v[jj][im] = c < C ? __ldcg(reinterpret_cast<const longlong2*>(base + (size_t)min(im, last_im) * img_stride))
+                            : make_longlong2(0, 0);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c = tt + 256 * (2 * half + jj);
+        if (c >= C) continue;
+        int slots, stride;
+        size_t img_stride;
+        const long long* base = chan_base(c, slots, stride, img_stride);
+#pragma unroll
+        for (int im = 0; im < IMGS; ++im) {
+          longlong2 a = v[jj][im];
+#pragma unroll 1
+          for (int sl = 1; sl < slots; ++sl) {      // slot mode only (B200SR3_STAT_SLOTS=1)
+            const longlong2 w = __ldcg(reinterpret_cast<const longlong2*>(base + (size_t)min(im, last_im) * img_stride + (size_t)sl * stride));
+            a.x += w.x; a.y += w.y;
+          }
+          gtab[im * gn_pitch + c + 2 * (c >> 3)] =
+              make_float2(__ll2float_rn(a.x) * (1.0f / 16777216.0f), __ll2float_rn(a.y) * (1.0f / 16777216.0f));
+        }
+      }
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (tt < IMGS * p.gn_groups) {
+      int im = 0, g = tt;
+      while (g >= p.gn_groups) { g -= p.gn_groups; ++im; }
+      float a = 0.f, d = 0.f;
+      for (int k = 0; k < cg; ++k) {
+        const int c = g * cg + k;
+        const float2 sv = gtab[im * gn_pitch + c + 2 * (c >> 3)];
+        a += sv.x; d += sv.y;
+      }
+      const float inv_n = 1.0f / ((float)(p.H * p.W) * (float)cg);
+      const float mean = a * inv_n;
+      gstat[tt] = make_float2(mean, rsqrtf(fmaxf(d * inv_n - mean * mean, 0.f) + 1e-5f));
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float hs = do_swish ? 0.5f : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tt + 256 * j;
+      if (c < C) {
+        int g = __float2int_rz(((float)c + 0.5f) * inv_cg);      // c / cg (exact: c < 1024, cg <= 64)
+#pragma unroll
+        for (int im = 0; im < IMGS; ++im) {
+          const float2 mr = gstat[im * p.gn_groups + g];
+          float2 v;
+          v.x = mr.y * gm[j];
+          v.y = bt[j] - mr.x * v.x;
+          v.x *= hs; v.y *= hs;
+          gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+        }
+      }
+    }
+  } else if (p.gn_stats0) {
     const int C = p.gn_C, C0 = p.gn_C0;
     const int cg = C / p.gn_groups;
     constexpr int TPG = IMGS == 1 ? 8 : (IMGS == 2 ? 4 : 1);
@@ -603,7 +701,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const int tt = warp < 4 ? (int)threadIdx.x : (int)threadIdx.x - 128;
     tab_b_early = tile0.b;
     halo_build_gn_table<G::IMGS>(p, reinterpret_cast<float2*>(smem_gen + S::GN_OFFSET), p.gn_C + 2 * (p.gn_C >> 3), tt,
-                                 tab_b_early, !PRELU && p.gn_swish != 0);
+                                 tab_b_early, !PRELU && p.gn_swish != 0, t_entry);
     if (HALO_DBG && tt == 0) p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_entry);   // [3] first table ready
   }
   if (GEO == 2) {
