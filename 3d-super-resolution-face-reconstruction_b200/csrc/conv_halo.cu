@@ -39,6 +39,8 @@ void conv_halo_init_device() {
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 2, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<64, 2, 0, 1>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<128, 1, 0, 1>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256, 1, true, 0, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<256, 1, 0, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, true, 1, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<64, 1, 1, 1>::TOTAL));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 1, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloSmem<128, 1, 1, 1>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HaloSmem<64, 1, 0, 1, true>::TOTAL));
   CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128, 1, true, 0, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -158,8 +160,10 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
                           srcs.size() <= 3),
           "halo conv: a stride-2 conv is one 3x3 source with parity-ordered weights (plus at most two 1x1 shortcut sources)");
   const bool prelu = prelu_slope != nullptr;      // transform = per-channel affine + PReLU (ArcFace), not GroupNorm + Swish
-  REQUIRE(!prelu || (gn != nullptr && !gn_from_stats && !tail && !upsample2x && !head),
-          "halo conv: the affine + PReLU transform takes a ready (scale, shift) row");
+  // (scale, shift) of the affine + PReLU transform: a ready row (`gn`, ArcFace's folded BatchNorm), or - `gn_from_stats` -
+  // the GroupNorm table the kernel builds per image, here WITHOUT the Swish (attn.norm, unet.py:117,127: slopes all 1)
+  REQUIRE(!prelu || (((gn != nullptr) != (gn_from_stats != nullptr)) && !tail && !upsample2x && !head),
+          "halo conv: the affine + PReLU transform takes a ready (scale, shift) row or a GroupNorm plan");
   REQUIRE(!partial_tiles || (!(stats && stats->partial) && !tail && !upsample2x),
           "halo conv: partial tiles are for convs that publish no statistics");
   REQUIRE(stride == 2 || !w.down_perm, "halo conv: parity-ordered weights belong to a stride-2 conv");
@@ -191,11 +195,15 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
   }
 
   // ---- segments; K order of the packed weights: [tap][all main channels] then the 1x1 shortcut blocks
+  // a 1x1 conv (the attention's qkv / out convs, unet.py:120-121): its first source is the conv's input ("main", one tap)
+  const bool conv1x1 = w.taps == 1;
+  REQUIRE(!conv1x1 || (srcs[0].ntaps == 1 && stride == 1 && !upsample2x && !tail && !head), "halo conv: a 1x1 conv reads 1x1 sources");
+  auto is_main = [&](size_t i) { return conv1x1 ? i == 0 : srcs[i].ntaps != 1; };
   int c_main = 0;
-  for (const HaloSource& s : srcs)
-    if (s.ntaps != 1) c_main += s.act.C;
+  for (size_t i = 0; i < srcs.size(); ++i)
+    if (is_main(i)) c_main += srcs[i].act.C;
   REQUIRE(c_main == w.cin_main && c_main % CONV_BLOCK_K == 0, "halo conv: main channel count mismatch");
-  const int main_taps = upsample2x ? 4 : 9;
+  const int main_taps = upsample2x ? 4 : (conv1x1 ? 1 : 9);
   int c_seen = 0, k_short = main_taps * c_main, kblocks = 0;
   bool any_gn = false;
   // tensor map of one source view: (C, Wd, Hd, B) with the given pixel strides, box = the geometry's halo
@@ -264,12 +272,12 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     sg.map = (int)i;
     sg.cblocks = a.C / CONV_BLOCK_K;
     sg.gn_off = s.gn_off;
-    if (s.ntaps != 1) {
+    if (is_main(i)) {
       REQUIRE(k_short == main_taps * c_main && kblocks == (c_seen / CONV_BLOCK_K) * main_taps,
               "halo conv: main sources must come first");
       sg.ntaps = main_taps;
-      sg.tap_w = upsample2x ? 2 : 3;
-      sg.pix0 = upsample2x ? -1 : 0;      // folded upsample: the 2x2 window depends on the output parity
+      sg.tap_w = upsample2x ? 2 : (conv1x1 ? 1 : 3);
+      sg.pix0 = upsample2x ? -1 : (conv1x1 ? pitch + 1 : 0);      // folded upsample: the 2x2 window depends on the output parity
       sg.k_base = c_seen;
       sg.k_tap_stride = c_main;
       c_seen += a.C;
@@ -371,7 +379,8 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       if (c[2] == 2 && c[0] < cg_min_bn) continue;
       if ((c[0] == 16) != (tail != nullptr)) continue;
       if (is_head && c[0] != 64) continue;
-      if (prelu && (c[2] != 1 || (c[1] == 2 && c[0] != 64))) continue;      // instantiated: (64,1) (64,2) (128,1) (256,1)
+      if (prelu && (c[2] != 1 || (c[1] == 2 && c[0] != 64))) continue;      // instantiated: (64,1) (64,2) (128,1) (256,1); two-image: (64,1) (128,1)
+      if (prelu && g2) continue;
       if (g1 && (c[1] != 1 || c[0] > 128)) continue;
       if (g2 && c[0] != 64) continue;
       if (c[0] == 128 && c[1] == 2 && !allow_128x2) continue;
@@ -446,14 +455,18 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     for (const HaloSource& s : srcs) {      // (a stride-2 conv has one 9-tap source: 9 C either way)
       // reference graph: full 3x3 at output resolution; a res_conv segment counts, an identity shortcut
       // that merely rides the GEMM (unet.py:101, nn.Identity) does not
-      if (!(s.ntaps == 1 && w.res_identity)) k += (double)s.ntaps * s.act.C;
+      if (!(s.identity || (s.ntaps == 1 && !conv1x1 && w.res_identity))) k += (double)s.ntaps * s.act.C;
       k_exec += (double)(s.ntaps == 1 ? 1 : main_taps) * s.act.C;
     }
     op.flops = 2.0 * m * (double)(tail ? tail->oc : out.C) * k;
     op.flops_executed = 2.0 * m * (double)out.C * k_exec;
   }
+  REQUIRE(!(prelu && g2), "halo conv: the affine + PReLU transform is not instantiated for the five-image geometry");
   op.run = [pp, grid, bn, mt, cg, any_gn, g1, g2, is_head, deep, prelu](cudaStream_t s) {
-    if (prelu) {
+    if (prelu && g1) {
+      if (bn == 128) launch_pdl(conv_halo_kernel<128, 1, true, 1, 1, false, false, true>, dim3(grid), dim3(halo_threads(128)), HaloSmem<128, 1, 1, 1>::TOTAL, s, *pp);
+      else launch_pdl(conv_halo_kernel<64, 1, true, 1, 1, false, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 1, 1, 1>::TOTAL, s, *pp);
+    } else if (prelu) {
       if (bn == 256) launch_pdl(conv_halo_kernel<256, 1, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(256)), HaloSmem<256, 1, 0, 1>::TOTAL, s, *pp);
       else if (bn == 128) launch_pdl(conv_halo_kernel<128, 1, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(128)), HaloSmem<128, 1, 0, 1>::TOTAL, s, *pp);
       else if (mt == 2) launch_pdl(conv_halo_kernel<64, 2, true, 0, 1, false, false, true>, dim3(grid), dim3(halo_threads(64)), HaloSmem<64, 2, 0, 1>::TOTAL, s, *pp);

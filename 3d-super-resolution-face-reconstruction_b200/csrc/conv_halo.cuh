@@ -529,7 +529,7 @@ template <int BLOCK_N, int MT, bool FUSE_GN, int GEO, int CG = 1, bool HEAD = fa
 __global__ void __launch_bounds__(halo_threads(BLOCK_N), 1)
 conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   using S = HaloSmem<BLOCK_N, MT, GEO, CG, DEEP>;
-  static_assert(!PRELU || (FUSE_GN && GEO == 0 && CG == 1 && !HEAD && !DEEP && BLOCK_N != 16), "affine + PReLU transform: plain GEO 0 shapes");
+  static_assert(!PRELU || (FUSE_GN && GEO != 2 && CG == 1 && !HEAD && !DEEP && BLOCK_N != 16), "affine + PReLU transform: plain one- / two-image shapes");
   static_assert(!DEEP || (GEO == 0 && MT == 1 && CG == 1 && !HEAD && (BLOCK_N == 64 || BLOCK_N == 128)), "deep ring: one-tile shapes");
   static_assert(CG == 1 || (CG == 2 && MT == 1 && GEO == 0 && BLOCK_N >= 64), "CTA pairs run one 8x16 tile per CTA");
   static_assert(!HEAD || (!FUSE_GN && GEO == 0 && CG == 1 && BLOCK_N == 64), "the head conv is a raw 3x3, Cout = 64");
@@ -1204,7 +1204,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       Tile t[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m) { t[m] = walk; tile_next(walk); }
-      if (FUSE_GN && (PRELU ? tab_b < 0 : t[0].b != tab_b)) {      // (the affine + PReLU table is the same for every image)
+      if (FUSE_GN && ((PRELU && !p.gn_stats0) ? tab_b < 0 : t[0].b != tab_b)) {      // (a ready affine + PReLU row is the same for every image)
         halo_build_gn_table<G::IMGS>(p, gtab, gn_pitch, tt, t[0].b, do_swish);
         tab_b = t[0].b;
       }

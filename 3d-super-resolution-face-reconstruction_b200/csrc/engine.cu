@@ -264,6 +264,8 @@ void Engine::finalize_weights(cudaStream_t s) {
     return p;
   };
   const int inner = cfg_.inner_channel;
+  ones_ = (float*)dalloc(1024 * sizeof(float));
+  launch_fill_f32(ones_, 1.f, 1024, s);
   wall_ = (float*)dalloc((size_t)noise_total_ * inner * sizeof(float));
   ball_ = (float*)dalloc((size_t)noise_total_ * sizeof(float));
   CUDA_CHECK(cudaMemsetAsync(wall_, 0, (size_t)noise_total_ * inner * sizeof(float), s));
@@ -593,7 +595,8 @@ void Engine::build_workspace(Workspace& ws) {
   // halo-resident conv (conv_halo.cuh): 3x3 main source(s) with the GroupNorm+Swish applied in shared
   // memory, raw 1x1 shortcut sources, GroupNorm statistics of the output from the epilogue
   auto conv_halo = [&](const std::string& name, const std::vector<HaloSource>& srcs, bool up, const PackedConv& w,
-                       const float* bias, int bias_stride, const GnRef& gn, int gn_C, bool want_stats, int stride = 1) {
+                       const float* bias, int bias_stride, const GnRef& gn, int gn_C, bool want_stats, int stride = 1,
+                       const float* affine_slope = nullptr) {      // non-null: GroupNorm WITHOUT Swish (slopes of 1)
     const Act& a0 = srcs[0].act;
     Act probe;
     probe.B = B; probe.H = up ? 2 * a0.H : a0.H / stride; probe.W = up ? 2 * a0.W : a0.W / stride; probe.C = w.cout;
@@ -602,8 +605,9 @@ void Engine::build_workspace(Workspace& ws) {
     st.partial = y.stats;
     st.slots = y.stat_slots;
     st.atomic = stat_atomic;
-    ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, true,
-                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get(), stride));
+    ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, affine_slope == nullptr,
+                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get(), stride, nullptr,
+                                       affine_slope));
     ws.n_conv++;
     return y;
   };
@@ -710,7 +714,7 @@ void Engine::build_workspace(Workspace& ws) {
                             true);
           const GnRef g2 = gn_table(l.name + ".block2", h, nullptr, rb + ".block2.block.0");
           // the shortcut (res_conv 1x1, or identity) is one or two extra raw 1x1 K segments of this GEMM
-          std::vector<HaloSource> s2{HaloSource{h, 9, 0}, HaloSource{xin, 1, -1}};
+          std::vector<HaloSource> s2{HaloSource{h, 9, 0}, HaloSource{xin, 1, -1, cin == l.cout}};      // (identity shortcut when dim == dim_out)
           if (is_up) s2.push_back(HaloSource{skip, 1, -1});
           cur = conv_halo(l.name + ".conv2", s2, false, c2, c2.bias, 0, g2, l.cout, true);
         } else {
@@ -724,16 +728,33 @@ void Engine::build_workspace(Workspace& ws) {
         }
         if (l.attn) {
           const Act ain = cur;
-          Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);
-          Act qkv = conv(l.name + ".attn.qkv", an, 1, 1, false, convs_.at(l.name + ".qkv"), nullptr, nullptr, nullptr,
-                         0, nullptr, ain.H, ain.W, false);
-          Act ao = act(ain.H, ain.W, ain.C);
-          ws.ops.push_back(Op{l.name + ".attn.core", false, [qkv, ao](cudaStream_t s) {
-            launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
-          }});
+          const PackedConv& pq = convs_.at(l.name + ".qkv");
           const PackedConv& po = convs_.at(l.name + ".out");
-          cur = conv(l.name + ".attn.out", ao, 1, 1, false, po, &ain, nullptr, po.bias, 0, nullptr, ain.H, ain.W,
-                     true);
+          static const bool attn_umma = [] { const char* e = getenv("B200SR3_ATTN_UMMA"); return e && e[0] == '1'; }();
+          GnRef ga;
+          const bool on_halo = use_halo_ && !attn_umma && !(ain.H == 4 && ain.W == 4) && ain.C <= 1024 &&
+                               conv_halo_eligible(ain.H, ain.W, ain.C % 64 == 0, pq.cout);
+          if (on_halo) ga = gn_table(l.name + ".attn", ain, nullptr, l.name + ".attn.norm");
+          if (on_halo && ga.plan) {
+            // SelfAttention (unet.py:113-142) with its two 1x1 convs on the halo kernel: attn.norm (GroupNorm, no Swish)
+            // is applied to the qkv conv's input tile in shared memory (the affine transform with slopes of 1), the
+            // residual `+ x` rides the out conv's GEMM as an identity K segment. No normalised tensor in HBM.
+            Act qkv = conv_halo(l.name + ".attn.qkv", {HaloSource{ain, 1, 0}}, false, pq, nullptr, 0, ga, ain.C, false, 1, ones_);
+            Act ao = act(ain.H, ain.W, ain.C);
+            ws.ops.push_back(Op{l.name + ".attn.core", false, [qkv, ao](cudaStream_t s) {
+              launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
+            }});
+            cur = conv_halo(l.name + ".attn.out", {HaloSource{ao, 1, -1}, HaloSource{ain, 1, -1, true}}, false, po, po.bias, 0,
+                            no_gn, 0, true);
+          } else {
+            Act an = group_norm(l.name + ".attn", ain, nullptr, l.name + ".attn.norm", false);
+            Act qkv = conv(l.name + ".attn.qkv", an, 1, 1, false, pq, nullptr, nullptr, nullptr, 0, nullptr, ain.H, ain.W, false);
+            Act ao = act(ain.H, ain.W, ain.C);
+            ws.ops.push_back(Op{l.name + ".attn.core", false, [qkv, ao](cudaStream_t s) {
+              launch_attention(qkv.ptr, ao.ptr, qkv.B, qkv.H * qkv.W, ao.C, s);
+            }});
+            cur = conv(l.name + ".attn.out", ao, 1, 1, false, po, &ain, nullptr, po.bias, 0, nullptr, ain.H, ain.W, true);
+          }
         }
         if (l.name.compare(0, 6, "downs.") == 0) feats.push_back(cur);
         break;

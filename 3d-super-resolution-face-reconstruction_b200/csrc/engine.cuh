@@ -147,6 +147,7 @@ class Engine {
   PackedConv tail_pc_;        // final_conv as a 16-row bf16 GEMM operand (halo conv tail)
   PackedConv head_pc_;        // downs.0 as a split-precision bf16 GEMM operand (halo conv head)
   float *wall_ = nullptr, *ball_ = nullptr;
+  float* ones_ = nullptr;     // 1024 ones: PReLU slopes of the affine-only (GroupNorm without Swish) transform
   std::vector<void*> owned_;
 
   int T_sched_ = 0;
@@ -190,8 +191,11 @@ void conv_init_device();
 // Halo-resident 3x3 conv with fused GroupNorm+Swish (conv_halo.cuh / conv_halo.cu).
 struct HaloSource {
   Act act;
-  int ntaps = 9;      // 9: 3x3 main source (folded to 4 parity taps when upsample2x); 1: raw 1x1 shortcut source
+  int ntaps = 9;      // 9: 3x3 main source (folded to 4 parity taps when upsample2x); 1: 1x1 source - a shortcut behind the
+                      // 3x3 sources, or, when the weights are a 1x1 conv (PackedConv::taps == 1), the conv's own input
   int gn_off = -1;    // channel offset in the GroupNorm (scale, shift) table; < 0: no transform
+  bool identity = false;   // 1x1 source whose weights are an identity matrix (a residual add riding the GEMM): executed,
+                           // but not a conv of the reference graph - no algorithmic FLOPs
 };
 bool conv_halo_eligible(int H, int W, int c_multiple_of_64_all, int cout);
 int conv_halo_stat_slots(const Act& out, bool upsample2x);

@@ -6,6 +6,7 @@ same sampler: each is read when the library builds its launch plan, so every var
   B200SR3_HEAD_PACK=1    head operand packed in HBM by its own kernel: same rows, same K order, BIT-identical
   B200SR3_DOWN_UMMA=1    Downsample convs on the first-generation kernel: another summation order, close
   B200SR3_NO_GRAPH=1     eager launches instead of the per-step CUDA graph: BIT-identical
+  B200SR3_ATTN_UMMA=1    attention: separate GroupNorm pass + 1x1 convs on the first-generation kernel: close
 """
 import hashlib
 import os
@@ -52,6 +53,8 @@ def test_switches_select_equivalent_paths(tmp_path):
         assert sha == base, name
     sha, _ = _run(tmp_path, "deep0", B200SR3_HALO_DEEP="0")
     assert sha == base, "B200SR3_HALO_DEEP=0"
-    sha, path = _run(tmp_path, "down_umma", B200SR3_DOWN_UMMA="1")
-    a, b = torch.load(base_path), torch.load(path)
-    assert float((a - b).abs().max()) <= 5e-3          # T=4 chain, different fp32 summation order in four convs
+    a = torch.load(base_path)
+    for name in ("B200SR3_DOWN_UMMA", "B200SR3_ATTN_UMMA"):
+        sha, path = _run(tmp_path, name, **{name: "1"})
+        b = torch.load(path)
+        assert float((a - b).abs().max()) <= 5e-3, name      # T=4 chain, another fp32 summation order in a few convs
