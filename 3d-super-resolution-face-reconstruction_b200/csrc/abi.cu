@@ -388,9 +388,11 @@ int b200sr3_conv_block(int device, const float* x0, int C0, const float* x1, int
       st.dbg = (unsigned long long*)dalloc(256 * 16 * sizeof(unsigned long long));
       CUDA_CHECK(cudaMemset(st.dbg, 0, 256 * 16 * sizeof(unsigned long long)));
     }
+    HaloConvExtra extra;
+    extra.gn_from_stats = gn_in_kernel ? &gplan : nullptr;
+    extra.stride = down ? 2 : 1;
     Op op = make_conv_halo_op("conv_block", srcs, up, pc, bias, 0, nullptr, out, gn, cin, swish != 0,
-                              (stats_out || timing) ? &st : nullptr, nullptr, nullptr, gn_in_kernel ? &gplan : nullptr,
-                              down ? 2 : 1);
+                              (stats_out || timing) ? &st : nullptr, extra);
     op.run(s);
     launch_nhwc_to_nchw(out.ptr, y, B, Cout, out.H, out.W, s);
     CUDA_CHECK(cudaStreamSynchronize(s));

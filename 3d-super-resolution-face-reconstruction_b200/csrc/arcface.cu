@@ -418,8 +418,10 @@ void MicaEncoder::build_plan(Plan& pl) {
     virt.B = B; virt.H = ARC_RES; virt.W = ARC_RES; virt.C = CONV_BLOCK_K;
     HaloHead hh;
     hh.cond = nullptr; hh.x = pl.blob; hh.cc = 0; hh.cx = 3;
+    HaloConvExtra ex;
+    ex.head = &hh;
     pl.ops.push_back(make_conv_halo_op("stem.conv1", {HaloSource{virt, 9, -1}}, false, stem_, stem_.bias, 0, nullptr, cur,
-                                       nullptr, 0, true, nullptr, nullptr, nullptr, nullptr, 1, &hh));
+                                       nullptr, 0, true, nullptr, ex));
     pl.ops.back().flops = 2.0 * B * ARC_RES * ARC_RES * 64.0 * 27.0;
     const float* slope = T_("arcface.prelu.weight");
     bf16* ptr = cur.ptr;
@@ -434,13 +436,19 @@ void MicaEncoder::build_plan(Plan& pl) {
     REQUIRE(cur.C == b.inplanes, "internal: arcface channel plan mismatch");
     // out = conv1(bn1(x)) with bn2 folded (arcface.py:60-62)
     Act t = act(cur.H, cur.W, b.planes);
+    HaloConvExtra e1;
+    e1.prelu_slope = ones_;           // bn1: affine only
+    e1.partial_tiles = true;
     pl.ops.push_back(make_conv_halo_op(b.name + ".conv1", {HaloSource{cur, 9, 0}}, false, b.c1, b.c1.bias, 0, nullptr, t, b.xf1,
-                                       b.inplanes, false, nullptr, nullptr, nullptr, nullptr, 1, nullptr, ones_, true));
+                                       b.inplanes, false, nullptr, e1));
     // out = conv2(prelu(out)) with bn3 folded, + identity / downsample(x) as K segments (arcface.py:63-69)
     Act y = act(cur.H / b.stride, cur.W / b.stride, b.planes);
-    pl.ops.push_back(make_conv_halo_op(b.name + ".conv2", {HaloSource{t, 9, 0}, HaloSource{cur, 1, -1}}, false, b.c2, b.c2.bias,
-                                       0, nullptr, y, b.xf2, b.planes, false, nullptr, nullptr, nullptr, nullptr, b.stride,
-                                       nullptr, b.slope2, true));
+    HaloConvExtra e2;
+    e2.prelu_slope = b.slope2;        // prelu in front of conv2
+    e2.partial_tiles = true;
+    e2.stride = b.stride;
+    pl.ops.push_back(make_conv_halo_op(b.name + ".conv2", {HaloSource{t, 9, 0}, HaloSource{cur, 1, -1, !b.down}}, false, b.c2,
+                                       b.c2.bias, 0, nullptr, y, b.xf2, b.planes, false, nullptr, e2));
     cur = y;
     pl.layer_out[b.name] = cur;
   }

@@ -148,9 +148,14 @@ int conv_halo_stat_slots(const Act& out, bool upsample2x) {
 
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
-                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloTail* tail,
-                     std::shared_ptr<ConvHaloParams>* params_out, const GnPlan* gn_from_stats, int stride,
-                     const HaloHead* head, const float* prelu_slope, bool partial_tiles) {
+                     const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats, const HaloConvExtra& extra) {
+  const HaloTail* tail = extra.tail;
+  std::shared_ptr<ConvHaloParams>* params_out = extra.params_out;
+  const GnPlan* gn_from_stats = extra.gn_from_stats;
+  const int stride = extra.stride;
+  const HaloHead* head = extra.head;
+  const float* prelu_slope = extra.prelu_slope;
+  const bool partial_tiles = extra.partial_tiles;
   REQUIRE(!srcs.empty() && (int)srcs.size() <= HALO_MAX_SEGS, "halo conv: 1..4 sources");
   const Act& a0 = srcs[0].act;
   REQUIRE(stride == 1 || stride == 2, "halo conv: stride 1 or 2");

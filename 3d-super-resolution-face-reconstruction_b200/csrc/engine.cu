@@ -605,9 +605,12 @@ void Engine::build_workspace(Workspace& ws) {
     st.partial = y.stats;
     st.slots = y.stat_slots;
     st.atomic = stat_atomic;
+    HaloConvExtra extra;
+    extra.gn_from_stats = gn.plan.get();
+    extra.stride = stride;
+    extra.prelu_slope = affine_slope;
     ws.ops.push_back(make_conv_halo_op(name, srcs, up, w, bias, bias_stride, ctl_, y, gn.tab, gn_C, affine_slope == nullptr,
-                                       want_stats ? &st : nullptr, nullptr, nullptr, gn.plan.get(), stride, nullptr,
-                                       affine_slope));
+                                       want_stats ? &st : nullptr, extra));
     ws.n_conv++;
     return y;
   };
@@ -643,8 +646,10 @@ void Engine::build_workspace(Workspace& ws) {
             st.partial = cur.stats;
             st.slots = cur.stat_slots;
             st.atomic = stat_atomic;
+            HaloConvExtra extra;
+            extra.head = &hh;
             ws.ops.push_back(make_conv_halo_op(l.name, {HaloSource{virt, 9, -1}}, false, head_pc_, T_(l.name + ".bias"), 0,
-                                               ctl_, cur, nullptr, 0, true, &st, nullptr, nullptr, nullptr, 1, &hh));
+                                               ctl_, cur, nullptr, 0, true, &st, extra));
             ws.n_conv++;
           }
           ws.ops.back().flops = 2.0 * B * R * R * (double)l.cout * 9.0 * l.c_x;      // reference graph: K = 9 * in_channel
@@ -767,9 +772,12 @@ void Engine::build_workspace(Workspace& ws) {
           o16.B = B; o16.H = cur.H; o16.W = cur.W; o16.C = 16;
           HaloTail tl;
           tl.x = ws.x; tl.eps_out = nullptr; tl.coefs = coefs_; tl.oc = oc;
+          HaloConvExtra extra;
+          extra.tail = &tl;
+          extra.params_out = &ws.tail_halo;
+          extra.gn_from_stats = g.plan.get();
           ws.ops.push_back(make_conv_halo_op(l.name + ".tail", {HaloSource{cur, 9, 0}}, false, tail_pc_,
-                                             T_(l.name + ".block.3.bias"), 0, ctl_, o16, g.tab, cur.C, true, nullptr, &tl,
-                                             &ws.tail_halo, g.plan.get()));
+                                             T_(l.name + ".block.3.bias"), 0, ctl_, o16, g.tab, cur.C, true, nullptr, extra));
           // HBM-bound: the bf16 activation in, the fp32 state read and written (Philox noise costs no bytes)
           ws.ops.back().bytes = (double)B * R * R * ((double)cur.C * 2.0 + (double)oc * 8.0);
           ws.n_conv++;

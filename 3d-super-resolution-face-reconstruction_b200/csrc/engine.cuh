@@ -210,15 +210,20 @@ struct HaloTail {      // final_conv fused with the sampler update (conv_halo.cu
   const float* coefs = nullptr;
   int oc = 3;
 };
+// Everything about a halo conv that most call sites leave at its default.
+struct HaloConvExtra {
+  const HaloTail* tail = nullptr;                        // final_conv + sampler update (BLOCK_N == 16)
+  std::shared_ptr<ConvHaloParams>* params_out = nullptr; // receives the launch parameters (the engine retargets the tail)
+  const GnPlan* gn_from_stats = nullptr;                 // non-null: the kernel builds the (scale, shift) table itself (gn ignored)
+  int stride = 1;                                        // 2: Downsample (unet.py:68-74), weights with down_perm
+  const HaloHead* head = nullptr;                        // non-null: downs.0 straight from the fp32 NCHW inputs
+  const float* prelu_slope = nullptr;                    // non-null: transform = (scale, shift) row or GroupNorm plan + PReLU slopes, no Swish
+  bool partial_tiles = false;                            // any H, W (no statistics): ArcFace's 56 / 28 / 14 / 7 px
+};
 Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& srcs, bool upsample2x,
                      const PackedConv& w, const float* bias, int bias_t_stride, const StepCtl* ctl, const Act& out,
                      const float2* gn, int gn_C, bool gn_swish, const ConvStats* stats,
-                     const HaloTail* tail = nullptr, std::shared_ptr<ConvHaloParams>* params_out = nullptr,
-                     const GnPlan* gn_from_stats = nullptr,    // non-null: the kernel builds the table itself (gn ignored)
-                     int stride = 1,                           // 2: Downsample (unet.py:68-74), weights with down_perm
-                     const struct HaloHead* head = nullptr,    // non-null: downs.0 straight from the fp32 NCHW inputs
-                     const float* prelu_slope = nullptr,       // non-null: transform = `gn` row (scale, shift) + PReLU slopes
-                     bool partial_tiles = false);              // any H, W (no statistics): ArcFace's 56 / 28 / 14 / 7 px
+                     const HaloConvExtra& extra = HaloConvExtra());
 void conv_halo_init_device();
 void halo_report_timing(const unsigned long long* dbg_dev, const char* label);
 // OIHW fp32 [Cout][Cin][3][3] -> bf16 [Cout][9*Cin] with the taps in PackedConv::down_perm order (engine.cu)
