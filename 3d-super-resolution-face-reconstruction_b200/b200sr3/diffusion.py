@@ -357,10 +357,11 @@ class GaussianDiffusion(nn.Module):
         return out.reshape((cond.shape[0], n) + tuple(out.shape[1:]))
 
     @torch.no_grad()
-    def sample_host(self, cond_host, out_host=None, seed=0, row_offset=0):
+    def sample_host(self, cond_host, out_host=None, seed=None, row_offset=0):
         """End-to-end call on HOST tensors (pinned for full PCIe speed): cond is copied to the
-        device, the full chain runs with Philox noise, the result is copied back; returns when
-        the copy has landed. This is the path bench.py reports as `e2e`."""
+        device, the full chain runs with Philox noise (`seed` as in sample_batched: None draws it from
+        torch's global generator), the result is copied back; returns when the copy has landed. This is
+        the path bench.py reports as `e2e`."""
         dev = self._sampling_device()
         eng = self._engine(dev)
         if cond_host.device.type != "cpu" or cond_host.dtype != torch.float32 or not cond_host.is_contiguous():
