@@ -166,6 +166,12 @@ struct alignas(64) ConvHaloParams {
   // 16 = no TMEM loads, 32 = no statistics math
   int pdl;                         // launched with the programmatic-dependent-launch attribute (B200SR3_PDL=1)
   int ablate;
+  // L2 prefetch of the NEXT conv's weights (constants): every CTA requests its slice [blockIdx.x * pf_slice, + pf_slice)
+  // of them while this kernel runs. In situ the first tile of a BLOCK_N = 256 layer waited ~16 % of its time for weight
+  // tiles (profiles/r02k_roles_in_situ.txt, `MMA waits W`): all 148 CTAs walk the weight matrix in the same order, so
+  // every tile's first request is an HBM miss that a three-stage ring cannot cover.
+  const uint8_t* pf_ptr;
+  unsigned pf_slice, pf_total;
   // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv_block): [grid][16] cycle counters
   unsigned long long* dbg;
 };
@@ -888,6 +894,19 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       if (HALO_DBG) {           // [12] kernel entry -> first MMA issued ("fill"), [13] entry -> last MMA issued
         p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(t_first_mma - t_entry);
         p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)(clock64() - t_entry);
+      }
+    }
+  } else if (warp == LW + 2) {
+    // ------------------------------------------------------------------ (TMEM allocator, otherwise idle) L2 prefetch
+    if (p.pf_ptr != nullptr && lane == 0) {
+      const unsigned off = blockIdx.x * p.pf_slice;
+      if (off < p.pf_total) {
+        __nanosleep(2000);      // behind this kernel's own first loads
+        const unsigned n = min(p.pf_slice, p.pf_total - off) & ~15u;
+        for (unsigned o = 0; o < n; o += 32768u) {
+          const unsigned sz = min(32768u, n - o);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + off + o), "r"(sz) : "memory");
+        }
       }
     }
   } else if (BLOCK_N == 16 && warp >= 4 && warp < 8) {

@@ -795,6 +795,18 @@ void Engine::build_workspace(Workspace& ws) {
     }
     if (l.kind != LayerKind::Final) ws.layer_out[l.name] = cur;
   }
+  // every halo conv prefetches the next conv's weights into L2 (the last one the first one's: the chain repeats per step)
+  static const bool no_prefetch = [] { const char* e = getenv("B200SR3_NO_WEIGHT_PREFETCH"); return e && e[0] == '1'; }();
+  if (!no_prefetch) {
+    const size_t n = ws.ops.size();
+    for (size_t i = 0; i < n; ++i) {
+      if (!ws.ops[i].set_prefetch) continue;
+      for (size_t d = 1; d <= n; ++d) {
+        const Op& nx = ws.ops[(i + d) % n];
+        if (nx.weights) { ws.ops[i].set_prefetch(nx.weights, nx.weight_bytes); break; }
+      }
+    }
+  }
 }
 
 void Engine::write_ctl(int t, int mode, const float* noise, uint64_t seed, long long numel, long long row0,

@@ -57,6 +57,9 @@ struct Op {
   double bytes = 0.0;   // algorithmic HBM bytes of one launch (HBM-bound kernels)
   double flops_executed = 0.0;   // what the tensor pipe runs: + identity-shortcut segments and K padding, - upsample folding
   std::function<void()> report;  // timing build only: prints (and resets) the launch's role counters
+  const void* weights = nullptr; // packed weights of this launch and their size: the PREVIOUS conv prefetches them into L2
+  size_t weight_bytes = 0;
+  std::function<void(const void*, size_t)> set_prefetch;   // (halo convs) which constants to prefetch while this launch runs
 };
 
 class Engine;
