@@ -497,6 +497,13 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
     else if (mt == 2) launch_halo<16, 2>(*pp, any_gn, grid, s);
     else launch_halo<16, 1>(*pp, any_gn, grid, s);
   };
+  op.weights = w.w;
+  op.weight_bytes = (size_t)w.cout * p.num_par * w.k_total * sizeof(bf16);
+  op.set_prefetch = [pp, grid](const void* ptr, size_t bytes) {
+    pp->pf_ptr = static_cast<const uint8_t*>(ptr);
+    pp->pf_total = (unsigned)std::min<size_t>(bytes, 64u << 20);
+    pp->pf_slice = (unsigned)(((pp->pf_total + grid - 1) / grid + 127) / 128 * 128);
+  };
 #if B200SR3_ROLE_TIMING
   // timing build: role counters of the launches named in B200SR3_TIMING_OPS ("all" or a comma-separated list of op
   // names), printed by Engine::profile_step (tools/profile_step.py)
