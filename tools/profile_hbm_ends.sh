@@ -8,4 +8,7 @@ timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k 
 echo "ncu tail rc $?"
 timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k 'regex:conv_halo_kernel<\(int\)64, \(int\)2, \(bool\)0, \(int\)0, \(int\)1, \(bool\)1' -s 50 -c 1 -o gpurun_out/${TAG}_head -f $CMD > gpurun_out/${TAG}_ncu_head.log 2>&1
 echo "ncu head rc $?"
-ls -la gpurun_out | grep ${TAG}; tail -3 gpurun_out/${TAG}_ncu_head.log
+for t in head tail; do
+  ncu -i gpurun_out/${TAG}_$t.ncu-rep --page raw --csv > gpurun_out/${TAG}_$t.raw.csv 2>/dev/null && rm -f gpurun_out/${TAG}_$t.ncu-rep
+done
+ls -la gpurun_out | grep ${TAG}
