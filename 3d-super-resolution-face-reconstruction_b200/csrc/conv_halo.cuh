@@ -190,6 +190,10 @@ struct HaloSmem {
   // 16 bytes of padding so that the eight groups a warp reads at once fall into different banks
   static constexpr int GN_BYTES = HaloGeo<GEO>::IMGS * 1024 * 10 + 2048;     // + (mean, rstd) of <= 5 x 32 groups
   static constexpr int GSTAT_OFFSET_IN_GN = HaloGeo<GEO>::IMGS * 1024 * 10;
+  // the current n tile's BLOCK_N bias values, staged by the epilogue warps (<= 1 KB, behind the <= 1280 B of group statistics
+  // that only the five-image geometry keeps)
+  static constexpr int BIAS_OFFSET_IN_GN = GSTAT_OFFSET_IN_GN + (HaloGeo<GEO>::IMGS == 5 ? 1280 : 0);
+  static_assert(BIAS_OFFSET_IN_GN + BLOCK_N * 4 <= GN_BYTES, "bias row must fit behind the GroupNorm table");
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;          // minus alignment slack and barriers
   static constexpr int W_FIT = (BUDGET - A_BYTES - STG_BYTES - GN_BYTES) / W_STAGE;
   static constexpr int W_STAGES = W_FIT > 12 ? 12 : W_FIT;
@@ -270,6 +274,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (FFMA2 / FADD2, sm_100): one issue slot for two IEEE round-to-nearest operations, bit-identical to
+// two scalar fmaf / adds. The transform and epilogue warps are bound by their own instruction latency (one or two warps per
+// scheduler), not by the FMA pipe, so halving the issue count of their arithmetic is what shortens them.
+__device__ __forceinline__ void fma2(float& dx, float& dy, float ax, float ay, float bx, float by, float cx, float cy) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(dx), "=f"(dy) : "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(cx), "f"(cy));
+}
+__device__ __forceinline__ void add2(float& dx, float& dy, float ax, float ay, float bx, float by) {
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(dx), "=f"(dy) : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -312,9 +328,21 @@ __device__ __forceinline__ void halo_head_row(const float* v, float* row) {
 #define HDBG_ACC(i) do { if (HALO_DBG) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
 #define HDBG_FLUSH(slot, n) do { if (HALO_DBG) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
+// Table slot of channel c (float index; one image's row starts at float2 index im * gn_pitch): 20 floats per 8 channels -
+// four (scale c, scale c+1, shift c, shift c+1) quads, so that a 16-byte load hands the transform two register PAIRS for
+// its packed FFMA2s, and 4 floats of padding, so that the eight 64-byte groups a warp reads at once fall into different banks.
+__device__ __forceinline__ int gn_tab_idx(int c) { return (c >> 3) * 20 + ((c & 6) << 1) + (c & 1); }
+__device__ __forceinline__ void gn_tab_put(float2* row, int c, float2 v) {
+  float* f = reinterpret_cast<float*>(row) + gn_tab_idx(c);
+  f[0] = v.x; f[2] = v.y;
+}
+__device__ __forceinline__ float2 gn_tab_get(const float2* row, int c) {
+  const float* f = reinterpret_cast<const float*>(row) + gn_tab_idx(c);
+  return make_float2(f[0], f[2]);
+}
+
 // (scale, shift) table of the fused GroupNorm for the IMGS images starting at image b0, built by the 256 transform threads
-// (tt = 0..255) into shared memory: gtab[im * gn_pitch + c + 2 * (c >> 3)] (10 float2 slots per 8 channels: the eight
-// 64-byte groups a warp reads at once fall into different banks).
+// (tt = 0..255) into shared memory, image im's row at gtab + im * gn_pitch, channel slots as gn_tab_idx says.
 // From the producers' statistics it is ONE pass with no intermediate barrier: TPG adjacent lanes own a (image, group).
 // Lane s takes the group's channels s, s + TPG, ...: for each it adds up the producer's int64 partial sums (exact, any
 // number of slots), converts to float and accumulates the group sums; a butterfly over the TPG lanes gives every lane
@@ -387,8 +415,8 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
             const longlong2 w = __ldcg(reinterpret_cast<const longlong2*>(base + (size_t)min(im, last_im) * img_stride + (size_t)sl * stride));
             a.x += w.x; a.y += w.y;
           }
-          gtab[im * gn_pitch + c + 2 * (c >> 3)] =
-              make_float2(__ll2float_rn(a.x) * (1.0f / 16777216.0f), __ll2float_rn(a.y) * (1.0f / 16777216.0f));
+          gn_tab_put(gtab + im * gn_pitch, c,
+                     make_float2(__ll2float_rn(a.x) * (1.0f / 16777216.0f), __ll2float_rn(a.y) * (1.0f / 16777216.0f)));
         }
       }
     }
@@ -399,7 +427,7 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
       float a = 0.f, d = 0.f;
       for (int k = 0; k < cg; ++k) {
         const int c = g * cg + k;
-        const float2 sv = gtab[im * gn_pitch + c + 2 * (c >> 3)];
+        const float2 sv = gn_tab_get(gtab + im * gn_pitch, c);
         a += sv.x; d += sv.y;
       }
       const float inv_n = 1.0f / ((float)(p.H * p.W) * (float)cg);
@@ -420,7 +448,7 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
           v.x = mr.y * gm[j];
           v.y = bt[j] - mr.x * v.x;
           v.x *= hs; v.y *= hs;
-          gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+          gn_tab_put(gtab + im * gn_pitch, c, v);
         }
       }
     }
@@ -504,7 +532,7 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
         v.x = rstd * gm;
         v.y = bt - mean * v.x;
         v.x *= hs; v.y *= hs;
-        gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+        gn_tab_put(gtab + im * gn_pitch, c, v);
       };
 #pragma unroll
       for (int q = 0; q < KEEP; ++q) {
@@ -519,7 +547,7 @@ __device__ __forceinline__ void halo_build_gn_table(const ConvHaloParams& p, flo
       const int c = idx - im * p.gn_C;
       float2 v = __ldg(p.gn + (size_t)min(b0 + im, p.B - 1) * p.gn_b_stride + c);
       if (do_swish) { v.x *= 0.5f; v.y *= 0.5f; }
-      gtab[im * gn_pitch + c + 2 * (c >> 3)] = v;
+      gn_tab_put(gtab + im * gn_pitch, c, v);
     }
   }
   asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -997,6 +1025,10 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
     const bool do_stats = p.stat_partial != nullptr;
     const float* bias = p.bias;
     if (bias && p.bias_t_stride) bias += (size_t)p.ctl->t * p.bias_t_stride;
+    // the n tile's bias row sits in shared memory: per 64-channel chunk a warp reads it with 16 broadcast LDS.128 instead of
+    // 16 global loads, each of which also cost a pair of descriptor moves (R2UR) inside this divergent region
+    float* bias_s = reinterpret_cast<float*>(smem_gen + S::GN_OFFSET + S::BIAS_OFFSET_IN_GN);
+    int bias_n0 = -1;
     constexpr int IMGS = G::IMGS;
     // this lane's columns (2l, 2l+1) of each 64-channel chunk, per image of the tile: sum0, sum1, sq0, sq1
     constexpr int NACC = GEO == 2 ? 2 : IMGS;      // GEO 2: a warp's rows touch at most two images
@@ -1037,6 +1069,12 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       ptx::tc_fence_after();
       const Tile t0 = walk;
       const int n0 = t0.n_tile * BLOCK_N;
+      if (bias && n0 != bias_n0) {          // (uniform over the epilogue warps: they walk the same super tiles)
+        HALO_EPI_SYNC();                    // every warp is done with the previous row
+        for (int i = tid_e; i < BLOCK_N; i += 128 * ESETS) bias_s[i] = __ldg(bias + n0 + i);
+        HALO_EPI_SYNC();
+        bias_n0 = n0;
+      }
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const Tile t = walk;
@@ -1076,8 +1114,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             if (bias) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc * 64 + half * 32 + j));
-                f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + cc * 64 + half * 32 + j);
+                add2(f[j], f[j + 1], f[j], f[j + 1], bv.x, bv.y);
+                add2(f[j + 2], f[j + 3], f[j + 2], f[j + 3], bv.z, bv.w);
               }
             }
 #pragma unroll
@@ -1121,8 +1160,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               const int im = (IMGS == 2) ? ((r >> 3) & 1) : 0;      // GEO 1: 8-row groups alternate between the images
               const uint32_t w = *reinterpret_cast<const uint32_t*>(slg + r * 128 + (((col_chunk ^ (uint32_t)(r & 7)) << 4) | col_word));
               const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
-              s0[im] += lo; q0[im] = fmaf(lo, lo, q0[im]);
-              s1[im] += hi; q1[im] = fmaf(hi, hi, q1[im]);
+              add2(s0[im], s1[im], s0[im], s1[im], lo, hi);
+              fma2(q0[im], q1[im], lo, hi, lo, hi, q0[im], q1[im]);
             }
 #pragma unroll
             for (int im = 0; im < IMGS; ++im) {
@@ -1248,7 +1287,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 v = g4[i];
-                sc[im][2 * i] = v.x; sh[im][2 * i] = v.y; sc[im][2 * i + 1] = v.z; sh[im][2 * i + 1] = v.w;
+                sc[im][2 * i] = v.x; sc[im][2 * i + 1] = v.y; sh[im][2 * i] = v.z; sh[im][2 * i + 1] = v.w;
               }
             }
           }
@@ -1341,21 +1380,24 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const float4 tv = g4[k];
-                    sc[0][2 * k] = tv.x; sh[0][2 * k] = tv.y; sc[0][2 * k + 1] = tv.z; sh[0][2 * k + 1] = tv.w;
+                    sc[0][2 * k] = tv.x; sc[0][2 * k + 1] = tv.y; sh[0][2 * k] = tv.z; sh[0][2 * k + 1] = tv.w;
                   }
                 }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float scv = sc[0][e], shv = sh[0][e];
-                  if (GEO == 1 && img[i] == 1) { scv = sc[NTAB - 1][e]; shv = sh[NTAB - 1][e]; }
+                for (int e = 0; e < 8; e += 2) {
+                  float sc0 = sc[0][e], sh0 = sh[0][e], sc1 = sc[0][e + 1], sh1 = sh[0][e + 1];
+                  if (GEO == 1 && img[i] == 1) { sc0 = sc[NTAB - 1][e]; sh0 = sh[NTAB - 1][e]; sc1 = sc[NTAB - 1][e + 1]; sh1 = sh[NTAB - 1][e + 1]; }
                   if (PRELU) {      // y = scale * prelu(x) + shift (arcface.py:60-64: bn1 before conv1, prelu before conv2)
-                    const float x = f[e];
-                    f[e] = fmaf(x > 0.f ? x : x * sl[e % (PRELU ? 8 : 1)], scv, shv);
+                    const float x0 = f[e], x1 = f[e + 1];
+                    fma2(f[e], f[e + 1], x0 > 0.f ? x0 : x0 * sl[e % (PRELU ? 8 : 1)], x1 > 0.f ? x1 : x1 * sl[(e + 1) % (PRELU ? 8 : 1)],
+                         sc0, sc1, sh0, sh1);
                     continue;
                   }
-                  const float h = fmaf(f[e], scv, shv);
+                  float h0, h1;
+                  fma2(h0, h1, f[e], f[e + 1], sc0, sc1, sh0, sh1);
                   // x*sigmoid(x) = h + h*tanh(h), h = x/2 (sc/sh arrive pre-halved): ONE MUFU per element
-                  f[e] = do_swish ? fmaf(h, tanh_approx(h), h) : h;
+                  if (do_swish) fma2(f[e], f[e + 1], h0, h1, tanh_approx(h0), tanh_approx(h1), h0, h1);
+                  else { f[e] = h0; f[e + 1] = h1; }
                 }
                 if (ok[i]) *ptr[i] = pack8(f);
               }
