@@ -1098,15 +1098,48 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               g2_dst = p.out + (((size_t)(t.b + img) * p.out_H + oy) * p.out_W + ox) * p.Cout + n0 + cc * 64;
             }
           }
+          // both 32-column halves of the chunk are requested before the one wait (a second wait cost a TMEM round trip)
+          // (only where the statistics accumulators leave 64 registers for it: elsewhere the second half is requested
+          // once the first has been packed)
+          constexpr bool LD64 = GEO != 2 && NACC * NCH <= 2;
+          uint32_t v2[2][32];
+          if (!HALO_ABLATE(16)) {
+            ptx::tmem_ld32(taddr + (uint32_t)(cc * 64), v2[0]);
+            if (LD64) ptx::tmem_ld32(taddr + (uint32_t)(cc * 64 + 32), v2[1]);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v2[0][j] = (uint32_t)j; v2[1][j] = (uint32_t)(32 + j); }
+          }
+          if (LD64 && ESETS == 1 && m == MT - 1 && cc == NCH - 1) {
+            // this thread's last TMEM read of the super tile has completed: hand the accumulator back to the MMA warp
+            // NOW, not after the store and the statistics of this chunk (in situ the MMA issuer of the 64 -> 64 layers and
+            // of the head waited 17-33 % of its time for this arrival, profiles/r03c_roles_in_situ.txt)
+            ptx::tc_fence_before();
+            if (CG == 2) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty(buf) & HALO_PEER_MASK);      // the leader's barrier
+            } else {
+              ptx::mbar_arrive(tmem_empty(buf));
+            }
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            if (!HALO_ABLATE(16)) {
-              ptx::tmem_ld32(taddr + (uint32_t)(cc * 64 + half * 32), v);
-              ptx::tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(half * 32 + j);
+            uint32_t* v = v2[LD64 ? half : 0];
+            if (!LD64 && half == 1) {
+              if (!HALO_ABLATE(16)) {
+                ptx::tmem_ld32(taddr + (uint32_t)(cc * 64 + 32), v);
+                ptx::tmem_ld_wait();
+              }
+              if (ESETS == 1 && m == MT - 1 && cc == NCH - 1) {
+                ptx::tc_fence_before();
+                if (CG == 2) {
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive_cluster(tmem_empty(buf) & HALO_PEER_MASK);
+                } else {
+                  ptx::mbar_arrive(tmem_empty(buf));
+                }
+              }
             }
             float f[32];
 #pragma unroll
@@ -1174,13 +1207,14 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           stg = (stg + 1 == NSTG) ? 0 : stg + 1;
         }
       }
-      // all of this thread's TMEM reads have completed: hand the accumulator back to the MMA warp
-      ptx::tc_fence_before();
-      if (CG == 2) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty(buf) & HALO_PEER_MASK);      // the leader's barrier
-      } else {
-        ptx::mbar_arrive(tmem_empty(buf));
+      if (ESETS != 1) {      // (two epilogue sets skip each other's chunks: release after the loop)
+        ptx::tc_fence_before();
+        if (CG == 2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty(buf) & HALO_PEER_MASK);      // the leader's barrier
+        } else {
+          ptx::mbar_arrive(tmem_empty(buf));
+        }
       }
 
       if (do_stats) {
