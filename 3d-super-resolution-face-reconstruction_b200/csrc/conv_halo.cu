@@ -425,6 +425,25 @@ Op make_conv_halo_op(const std::string& name, const std::vector<HaloSource>& src
       else if (bn == 128 && mt == 1 && ((sc_blocks >= 1 && main_blocks <= 2) || force == 1)) deep = true;
     }
   }
+  // Resident weights (conv_halo.cuh, ConvHaloParams::w_resident): one-tile, three-stage shape whose 12-stage weight ring
+  // holds every weight tile of the layer. OPT-IN (B200SR3_W_RESIDENT=1; =2 restricts it to layers without 1x1 shortcut
+  // segments over a concatenated input): measured and rejected - the only shape with room for all weight tiles gives up the
+  // two-tile super tiles / the deep halo ring, and that costs more than the weight stream (same box, profiles/r03u_ab.txt:
+  // 64 -> 64 53.3 -> 59.2 us, + identity 61.0 -> 67.3, + res128 80.6 -> 99.2, + res192 89.2 -> 113.5; identical results).
+  p.w_resident = 0;
+  {
+    int n_w = 0, sc_blocks = 0;
+    for (int i = 0; i < p.num_segs; ++i) {
+      n_w += p.seg[i].cblocks * p.seg[i].ntaps;
+      if (p.seg[i].ntaps == 1) sc_blocks += p.seg[i].cblocks;
+    }
+    const char* e = getenv("B200SR3_W_RESIDENT");
+    const int mode = e ? atoi(e) : 0;
+    static_assert(HaloSmem<64, 1, 0, 1, false>::W_STAGES >= 12, "resident weights count on a 12-stage ring");
+    const bool can = !g1 && !g2 && cg == 1 && !tail && !is_head && !prelu && bn == 64 && out.C == 64 && p.num_par == 1 &&
+                     n_w <= 12 && !getenv("B200SR3_HALO_BN") && !getenv("B200SR3_HALO_MT");
+    if (can && mode != 0 && !(mode == 2 && sc_blocks >= 2)) { deep = false; mt = 1; p.w_resident = n_w; }
+  }
   p.tiles_n = out.C / bn;
   p.total_super = (int)(m_tiles / (mt * cg) * p.tiles_n);
   p.seg_len_super = (int)(tiles_img * p.num_par / (mt * cg));

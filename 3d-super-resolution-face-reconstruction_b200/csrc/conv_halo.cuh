@@ -172,6 +172,14 @@ struct alignas(64) ConvHaloParams {
   // every tile's first request is an HBM miss that a three-stage ring cannot cover.
   const uint8_t* pf_ptr;
   unsigned pf_slice, pf_total;
+  // Resident weights (0: off, else the number of weight tiles a super tile walks, <= the ring's stages): every super tile
+  // of the launch uses the SAME weight tiles (one n tile, one parity) and they all fit the ring, so the producer loads them
+  // once per CTA and the MMA issuer neither waits for nor recycles a stage after the first super tile. With no weight loads
+  // at all the 64 -> 64 layers at 128^2 ran 11-13 % faster and left the power cap (tools/ablate_loads.sh): their weight
+  // stream (74 KB per super tile through L2 -> shared memory) competes with the MMAs' operand reads for the port. Opt-in
+  // only: the one shape with room for 12 resident tiles has one-tile super tiles and a three-stage halo ring, and is slower
+  // (conv_halo.cu, profiles/r03u_ab.txt).
+  int w_resident;
   // optional role timing (B200SR3_CONV_TIMING=1 in b200sr3_conv_block): [grid][16] cycle counters
   unsigned long long* dbg;
 };
@@ -326,6 +334,13 @@ __device__ __forceinline__ void halo_head_row(const float* v, float* row) {
 #define HDBG_DECL() unsigned long long hd[4] = {0ull, 0ull, 0ull, 0ull}; long long hd_t0 = 0
 #define HDBG_T0() do { if (HALO_DBG) hd_t0 = clock64(); } while (0)
 #define HDBG_ACC(i) do { if (HALO_DBG) hd[i] += (unsigned long long)(clock64() - hd_t0); } while (0)
+#ifdef HALO_EPI_PROFILE      // one-off experiment: the epilogue's sections take the transform's counter slots
+#define HEPI_T0() HDBG_T0()
+#define HEPI_ACC(i) do { HDBG_ACC(i); HDBG_T0(); } while (0)
+#else
+#define HEPI_T0() do { } while (0)
+#define HEPI_ACC(i) do { } while (0)
+#endif
 #define HDBG_FLUSH(slot, n) do { if (HALO_DBG) for (int _i = 0; _i < (n); ++_i) p.dbg[blockIdx.x * 16 + (slot) + _i] = hd[_i]; } while (0)
 
 // Table slot of channel c (float index; one image's row starts at float2 index im * gn_pitch): 20 floats per 8 channels -
@@ -830,6 +845,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
             }
           }
         }
+        if (p.w_resident) break;      // every later super tile finds its weight tiles where the first one left them
       }
     }
   } else if (warp == LW + 3) {
@@ -854,6 +870,8 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       long long t_first_mma = 0;
       const bool dbg_on = HALO_DBG;
       uint32_t b_cur = w_lo0, w_full_cur = w_full(0), w_empty_cur = w_empty(0);      // running per-stage values of ws
+      const int wres = p.w_resident;
+      const int wst_eff = wres ? wres : WST;      // resident: stage j holds tile j of EVERY super tile, phase 0 stays complete
       Tile walk = tile0;
       for (int sup = sup_begin; sup < sup_end; ++sup, ++it) {
         const int buf = it & 1;
@@ -890,7 +908,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               const uint32_t b_lo = b_cur;
               const uint32_t wcur = w_empty_cur;
               b_cur += (uint32_t)(S::W_STAGE >> 4); w_full_cur += 8u; w_empty_cur += 8u;
-              if (++ws == WST) { ws = 0; wphase ^= 1u; b_cur = w_lo0; w_full_cur = w_full(0); w_empty_cur = w_empty(0); }
+              if (++ws == wst_eff) { ws = 0; if (!wres) wphase ^= 1u; b_cur = w_lo0; w_full_cur = w_full(0); w_empty_cur = w_empty(0); }
               ready = ptx::mbar_test_wait(w_full_cur, wphase);      // look one stage ahead
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
@@ -904,7 +922,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
                                    desc(b_lo + 2u * k, B_HI), idesc, accum | (uint32_t)k);
                 }
               }
-              if (CG == 2) umma_commit_pair(wcur); else ptx::umma_commit(wcur);
+              if (CG == 2) umma_commit_pair(wcur); else if (!wres) ptx::umma_commit(wcur);
               accum = 1;
               a_lo += 8u;
               if (++tx == ntx) { tx = 0; a_lo += (uint32_t)(G::PITCH - ntx) * 8u; }
@@ -1088,6 +1106,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
           // the tensor store that last read this slab must have finished reading it
           if (lane == 0) bulk_wait_read<NSTG - 1>();
           __syncwarp();
+          HEPI_T0();
           bf16* g2_dst = nullptr;             // GEO 2: this thread's output row in global memory (null: not an output)
           if (GEO == 2 && ((g2_valid >> lane) & 1u) && !HALO_ABLATE(1)) {
             const int img = g2_first + (lane >= g2_rb ? 1 : 0);
@@ -1111,6 +1130,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v2[0][j] = (uint32_t)j; v2[1][j] = (uint32_t)(32 + j); }
           }
+          HEPI_ACC(1);
           if (LD64 && ESETS == 1 && m == MT - 1 && cc == NCH - 1) {
             // this thread's last TMEM read of the super tile has completed: hand the accumulator back to the MMA warp
             // NOW, not after the store and the statistics of this chunk (in situ the MMA issuer of the 64 -> 64 layers and
@@ -1159,6 +1179,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               if (GEO == 2 && g2_dst) *reinterpret_cast<uint4*>(g2_dst + (half * 4 + j) * 8) = pk;
             }
           }
+          HEPI_ACC(2);
           fence_proxy_async_smem();       // generic-proxy writes -> visible to the TMA store
           if (GEO == 2) {
             __syncwarp();                   // rows were stored from registers; the slab only feeds the statistics
@@ -1184,6 +1205,7 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
               else { acc[0][cc][0] += i0; acc[0][cc][1] += i1; acc[0][cc][2] += i2; acc[0][cc][3] += i3; }
             }
           }
+          HEPI_ACC(3);
           if (GEO != 2 && do_stats && !HALO_ABLATE(32)) {
             float s0[IMGS], s1[IMGS], q0[IMGS], q1[IMGS];
 #pragma unroll
@@ -1271,7 +1293,11 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
       }
     }
     if (lane == 0) bulk_wait_all();       // the staging slabs must outlive the stores that read them
+#ifdef HALO_EPI_PROFILE
+    if (tid_e == 0) HDBG_FLUSH(8, 4);      // [8] waits accumulator, [9] waits slab, [10] load + pack + store, [11] statistics
+#else
     if (tid_e == 0) HDBG_FLUSH(8, 1);      // [8] epilogue waits accumulator
+#endif
     if (tid_e == 0 && HALO_DBG) p.dbg[blockIdx.x * 16 + 14] = (unsigned long long)(clock64() - t_entry);   // [14] entry -> epilogue done
 #undef HALO_EPI_SYNC
   } else if (XF && (warp < 4 || (warp >= 8 && warp < 12))) {
@@ -1449,7 +1475,9 @@ conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
         }
       }
     }
+#ifndef HALO_EPI_PROFILE
     if (tt == 0) HDBG_FLUSH(10, 2);      // [10] transform waits A full (incl. table loads), [11] transforming
+#endif
   }
 
   ptx::tc_fence_before();

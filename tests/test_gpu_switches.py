@@ -7,6 +7,8 @@ same sampler: each is read when the library builds its launch plan, so every var
   B200SR3_DOWN_UMMA=1    Downsample convs on the first-generation kernel: another summation order, close
   B200SR3_NO_GRAPH=1     eager launches instead of the per-step CUDA graph: BIT-identical
   B200SR3_ATTN_UMMA=1    attention: separate GroupNorm pass + 1x1 convs on the first-generation kernel: close
+  B200SR3_W_RESIDENT=1   (opt-in, rejected on speed) Cout = 64 layers keep all weight tiles in shared memory: same K order
+                         per tile, BIT-identical
 """
 import hashlib
 import os
@@ -48,7 +50,7 @@ def _run(tmp_path, tag, **env):
 def test_switches_select_equivalent_paths(tmp_path):
     import torch
     base, base_path = _run(tmp_path, "default")
-    for name in ("B200SR3_STAT_SLOTS", "B200SR3_HEAD_PACK", "B200SR3_NO_GRAPH"):
+    for name in ("B200SR3_STAT_SLOTS", "B200SR3_HEAD_PACK", "B200SR3_NO_GRAPH", "B200SR3_W_RESIDENT"):
         sha, _ = _run(tmp_path, name, **{name: "1"})
         assert sha == base, name
     sha, _ = _run(tmp_path, "deep0", B200SR3_HALO_DEEP="0")
